@@ -1,0 +1,751 @@
+// bgmm_engine.cu -- auxiliary kernels + the C-ABI (include/bgmm_b200.h) of libbgmm_b200.so.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a (see __graft_entry__.build()).
+#include "bgmm_ops.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+
+// =============================================================================================
+// auxiliary kernels
+// =============================================================================================
+
+// Initial build of the sufficient statistics in the reference's order (gaussian_components.py:109-111:
+// for k ascending, for i ascending with z[i]==k: add_item).  One CTA per component, one thread per
+// statistic entry, serial over the component's members so every sum is accumulated in the same order
+// as the reference (bit-identical).  idx: data indices bucketed by component, ascending inside a bucket.
+template <int COV>
+__global__ void k_build_stats(const Params p, const long long *__restrict__ idx, const long long *__restrict__ start,
+                              int DP) {
+    const int k = blockIdx.x;
+    const int D = p.D;
+    const int SS = stat_len(DP, COV);
+    const long long lo = start[k], hi = start[k + 1];
+    const int nel = (COV == COV_FULL ? packed_len(D) : D) + D;
+    for (int e = threadIdx.x; e < nel; e += blockDim.x) {
+        int a, b;
+        bool is_num = false;
+        if (COV == COV_FULL) {
+            if (e < packed_len(D)) decode_row_idx(e, a, b);
+            else { is_num = true; a = b = e - packed_len(D); }
+        } else {
+            if (e < D) { a = b = e; }
+            else { is_num = true; a = b = e - D; }
+        }
+        double acc;
+        if (is_num) acc = __dmul_rn(p.k0, p.m0[a]);
+        else acc = __dadd_rn(p.S0[COV == COV_FULL ? row_idx(a, b) : a], __dmul_rn(p.k0, __dmul_rn(p.m0[a], p.m0[b])));
+        for (long long t = lo; t < hi; ++t) {
+            const long long i = idx[t];
+            const double xa = p.X[(size_t)i * DP + a];
+            if (is_num) acc = __dadd_rn(acc, xa);
+            else acc = __dadd_rn(acc, __dmul_rn(xa, p.X[(size_t)i * DP + b]));
+        }
+        if (is_num) p.num[(size_t)k * DP + a] = acc;
+        else p.S[(size_t)k * SS + (COV == COV_FULL ? row_idx(a, b) : a)] = acc;
+    }
+}
+
+__global__ void k_relabel(const int *__restrict__ z_uid, const int *__restrict__ slot_of_uid, long long N,
+                          long long *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int uid = z_uid[i];
+    out[i] = uid < 0 ? -1LL : (long long)slot_of_uid[uid];
+}
+
+__global__ void k_philox(double *__restrict__ u, long long N, unsigned long long seed, unsigned long long sweep) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < N) u[j] = philox_uniform(seed, sweep, (unsigned long long)j);
+}
+
+// log_marg_k for every live component (gaussian_components.py:253-276 / _diag.py:271-289); one warp each
+template <int COV>
+__global__ void k_log_marg_k(const Params p, int DP, double logdet_S0, double *__restrict__ out) {
+    extern __shared__ __align__(16) double A[];
+    const int k = blockIdx.x, lane = threadIdx.x & 31;
+    const int D = p.D;
+    const long long n = p.counts[k];
+    const double kap = p.k0 + (double)n;
+    const long long vN = p.v0 + n;
+    const double *num = p.num + (size_t)k * DP;
+    const double *S = p.S + (size_t)k * stat_len(DP, COV);
+    double ldN = 0.0;
+    bool bad = false;
+    if (COV == COV_FULL) {
+        for (int a = 0; a < D; ++a) {
+            const double ma = num[a] / kap;
+            for (int b = lane; b <= a; b += 32) A[row_idx(a, b)] = S[row_idx(a, b)] - kap * (ma * (num[b] / kap));
+        }
+        __syncwarp();
+        for (int j = 0; j < D; ++j) {
+            const double ajj = A[row_idx(j, j)];
+            if (!(ajj > 0.0)) { bad = true; break; }
+            const double inv = 1.0 / sqrt(ajj);
+            ldN += log(ajj);
+            __syncwarp();
+            for (int a = j + 1 + lane; a < D; a += 32) A[row_idx(a, j)] *= inv;
+            __syncwarp();
+            for (int a = j + 1 + lane; a < D; a += 32) {
+                const double laj = A[row_idx(a, j)];
+                for (int b = j + 1; b <= a; ++b) A[row_idx(a, b)] = fma(-laj, A[row_idx(b, j)], A[row_idx(a, b)]);
+            }
+            __syncwarp();
+        }
+    } else {
+        for (int a = 0; a < D; ++a) {
+            const double m = num[a] / kap;
+            const double sn = S[a] - kap * (m * m);
+            if (!(sn > 0.0)) bad = true;
+            ldN += log(sn);
+        }
+    }
+    if (lane == 0) {
+        double r;
+        if (bad) {
+            r = NAN;
+        } else if (COV == COV_FULL) {
+            double g = 0.0;
+            for (int j = 1; j <= D; ++j) g += p.lgam[vN + 1 - j] - p.lgam[p.v0 + 1 - j];
+            r = -(double)n * D / 2. * p.log_pi + D / 2. * log(p.k0) - D / 2. * log(kap) + p.v0 / 2. * logdet_S0 -
+                vN / 2. * ldN + g;
+        } else {
+            r = -(double)n * D / 2. * p.log_pi + D / 2. * log(p.k0) - D / 2. * log(kap) + p.v0 / 2. * logdet_S0 -
+                vN / 2. * ldN + D * (p.lgam[vN] - p.lgam[p.v0]);
+        }
+        out[k] = r;
+    }
+}
+
+// inv_covars / logdet_covars views (gaussian_components.py:88-89) reconstructed from the Cholesky record:
+// inv = L^-T L^-1.  One warp per component; W (D x D) in shared memory.
+template <int COV>
+__global__ void k_inv_covar(const Params p, int DP, double *__restrict__ logdet_out, double *__restrict__ inv_out) {
+    extern __shared__ __align__(16) double W[];
+    const int k = blockIdx.x, lane = threadIdx.x & 31;
+    const int D = p.D;
+    const int R = rec_len(DP, COV);
+    const double *rec = p.rec + (size_t)k * R;
+    if (lane == 0) logdet_out[k] = rec[rec_sc_off(DP, COV) + SC_LOGDET];
+    if (COV == COV_DIAG) {
+        for (int a = lane; a < D; a += 32) inv_out[(size_t)k * D + a] = rec[DP + a];
+        return;
+    }
+    // column e of W = L^-1: forward substitution on the unit vector e_e
+    for (int e = lane; e < D; e += 32) {
+        for (int a = 0; a < D; ++a) {
+            double s = (a == e) ? 1.0 : 0.0;
+            for (int b = e; b < a; ++b) s -= rec[col_off(DP, b) + (a - b)] * W[b * D + e];
+            W[a * D + e] = (a < e) ? 0.0 : s * rec[col_off(DP, a)];
+        }
+    }
+    __syncwarp();
+    for (int t = lane; t < D * D; t += 32) {
+        const int a = t / D, b = t % D;
+        double s = 0.0;
+        for (int c = max(a, b); c < D; ++c) s += W[c * D + a] * W[c * D + b];
+        inv_out[(size_t)k * D * D + t] = s;
+    }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static thread_local std::string g_err;
+int bgmm_fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+static int fail(int code, const std::string &msg) { return bgmm_fail(code, msg); }
+static int pad_dim(int D) {
+    int dp = 1;
+    while (dp < D) dp <<= 1;
+    return dp;
+}
+
+// one getter per instantiation unit (csrc/inst/*.cu, generated); BGMM_HAVE_D<dp> says which were built
+#define DECL(dp) const Ops *bgmm_ops_full_##dp(int (**prep)(bgmm_handle *)); const Ops *bgmm_ops_diag_##dp(int (**prep)(bgmm_handle *));
+DECL(1) DECL(2) DECL(4) DECL(8) DECL(16) DECL(32) DECL(64)
+#undef DECL
+static const Ops *pick_ops(int cov, int DP, int (**prep)(bgmm_handle *)) {
+    switch (DP) {
+#define CASE(dp) case dp: return cov == BGMM_COV_FULL ? bgmm_ops_full_##dp(prep) : bgmm_ops_diag_##dp(prep);
+#ifdef BGMM_HAVE_D1
+        CASE(1)
+#endif
+#ifdef BGMM_HAVE_D2
+        CASE(2)
+#endif
+#ifdef BGMM_HAVE_D4
+        CASE(4)
+#endif
+#ifdef BGMM_HAVE_D8
+        CASE(8)
+#endif
+#ifdef BGMM_HAVE_D16
+        CASE(16)
+#endif
+#ifdef BGMM_HAVE_D32
+        CASE(32)
+#endif
+#ifdef BGMM_HAVE_D64
+        CASE(64)
+#endif
+#undef CASE
+    }
+    return nullptr;
+}
+
+static void free_all(bgmm_handle *h) {
+    cudaFree(h->dX); cudaFree(h->d_log_prior); cudaFree(h->d_lgam); cudaFree(h->d_logv); cudaFree(h->d_m0);
+    cudaFree(h->d_S0); cudaFree(h->d_z); cudaFree(h->d_slot_of_uid); cudaFree(h->d_uid_of_slot); cudaFree(h->d_uid_free);
+    cudaFree(h->d_counts); cudaFree(h->d_num); cudaFree(h->d_S); cudaFree(h->d_rec); cudaFree(h->d_wbuf);
+    cudaFree(h->d_rec_prior); cudaFree(h->d_ctl); cudaFree(h->d_err); cudaFree(h->d_u); cudaFree(h->d_order);
+    cudaFree(h->d_tmp_ll);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+}
+
+static int check_dev_err(bgmm_handle *h, const char *what) {
+    int e = 0;
+    CU(cudaMemcpyAsync(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (e != 0) {
+        int zero = 0;
+        cudaMemcpyAsync(h->d_err, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+        return fail(e, std::string(what) + ": covariance not positive definite");
+    }
+    return 0;
+}
+
+extern "C" {
+
+const char *bgmm_version(void) { return "pybgmm-b200 0.1.0 (sm_100a)"; }
+const char *bgmm_last_error(void) { return g_err.c_str(); }
+int bgmm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const double *m0, double k0, int64_t v0,
+                const double *S0, int32_t K_max, const double *lgamma_half_tab, const double *log_tab, int64_t tab_len,
+                int32_t device, bgmm_t **out) {
+    if (!out) return fail(BGMM_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!X || !m0 || !S0) return fail(BGMM_EINVAL, "X, m0, S0 must not be NULL");
+    if (N < 1 || D < 1) return fail(BGMM_EINVAL, "N and D must be >= 1");
+    if (D > 64) return fail(BGMM_EINVAL, "D > 64 is not supported by this build");
+    if (cov_type != BGMM_COV_FULL && cov_type != BGMM_COV_DIAG) return fail(BGMM_EINVAL, "invalid covariance type");
+    if (v0 < D) return fail(BGMM_EINVAL, "v_0 must be >= D (prior/niw.py:21)");
+    if (!(k0 > 0.0)) return fail(BGMM_EINVAL, "k_0 must be > 0");
+    if (K_max < 1 || K_max > 4096) return fail(BGMM_EINVAL, "K_max must be in [1, 4096]");
+    if (N >= (1LL << 31)) return fail(BGMM_EINVAL, "N must be < 2^31");
+    const int64_t need = v0 + N + 2;
+    if ((lgamma_half_tab || log_tab) && (!lgamma_half_tab || !log_tab || tab_len < need))
+        return fail(BGMM_EINVAL, "lgamma/log tables must both be given with tab_len >= v0 + N + 2");
+    if (bgmm_device_count() <= device || device < 0)
+        return fail(BGMM_ENODEV, "no CUDA device " + std::to_string(device) + " (this library has no CPU fallback)");
+    CU(cudaSetDevice(device));
+
+    bgmm_handle *h = new bgmm_handle();
+    h->device = device; h->N = N; h->D = D; h->DP = pad_dim(D); h->cov = cov_type; h->K_max = K_max;
+    h->k0 = k0; h->v0 = v0;
+    const int DP = h->DP;
+    int (*prep)(bgmm_handle *) = nullptr;
+    h->ops = pick_ops(cov_type, DP, &prep);
+    if (!h->ops) { delete h; return fail(BGMM_EINVAL, "this build has no kernels for D=" + std::to_string(D)); }
+    const int SS = stat_len(DP, cov_type);
+    const int R = h->ops->rec_len;
+
+    // prior, padded / packed
+    h->m0.assign(DP, 0.0);
+    for (int a = 0; a < D; ++a) h->m0[a] = m0[a];
+    h->S0p.assign(SS, 0.0);
+    if (cov_type == BGMM_COV_FULL) {
+        for (int a = 0; a < D; ++a)
+            for (int b = 0; b <= a; ++b) h->S0p[row_idx(a, b)] = S0[a * D + b];
+        // log|S_0| for log_marg_k (gaussian_components.py:271): Cholesky on the host (prior constant)
+        std::vector<double> A(D * D);
+        for (int a = 0; a < D; ++a) for (int b = 0; b < D; ++b) A[a * D + b] = S0[a * D + b];
+        double ld = 0.0;
+        for (int j = 0; j < D; ++j) {
+            double d = A[j * D + j];
+            for (int c = 0; c < j; ++c) d -= A[j * D + c] * A[j * D + c];
+            if (!(d > 0.0)) { delete h; return fail(BGMM_ENUMERIC, "S_0 is not positive definite"); }
+            const double l = sqrt(d);
+            A[j * D + j] = l;
+            ld += 2.0 * log(l);
+            for (int a = j + 1; a < D; ++a) {
+                double s = A[a * D + j];
+                for (int c = 0; c < j; ++c) s -= A[a * D + c] * A[j * D + c];
+                A[a * D + j] = s / l;
+            }
+        }
+        h->logdet_S0 = ld;
+    } else {
+        double ld = 0.0;
+        for (int a = 0; a < D; ++a) {
+            if (!(S0[a] > 0.0)) { delete h; return fail(BGMM_ENUMERIC, "S_0 must be positive"); }
+            h->S0p[a] = S0[a];
+            ld += log(S0[a]);
+        }
+        h->logdet_S0 = ld;
+    }
+
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    h->grid = h->num_sms;
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    const size_t fixed = h->ops->smem_fixed(D, K_max);
+    if (fixed + 1024 > smem_max) { delete h; return fail(BGMM_EINVAL, "K_max too large for shared memory"); }
+    size_t kc = (smem_max - fixed - 64) / ((size_t)R * sizeof(double));
+    if (kc > (size_t)K_max) kc = K_max;
+    h->Kc = (int)kc;
+    h->smem_bytes = fixed + (size_t)h->Kc * R * sizeof(double) + 32;
+    h->smem_item = fixed + 32;
+    if (int rc = prep(h)) { delete h; return rc; }
+
+#define ALLOC(ptr, bytes)                                                                             \
+    do {                                                                                              \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                                        \
+        if (e_ != cudaSuccess) {                                                                      \
+            free_all(h); delete h;                                                                    \
+            return fail(BGMM_ENOMEM, std::string("cudaMalloc ") + #ptr + ": " + cudaGetErrorString(e_)); \
+        }                                                                                             \
+    } while (0)
+    ALLOC(h->dX, sizeof(double) * (size_t)N * DP);
+    ALLOC(h->d_log_prior, sizeof(double) * (size_t)N);
+    ALLOC(h->d_lgam, sizeof(double) * (size_t)need);
+    ALLOC(h->d_logv, sizeof(double) * (size_t)need);
+    ALLOC(h->d_m0, sizeof(double) * DP);
+    ALLOC(h->d_S0, sizeof(double) * SS);
+    ALLOC(h->d_z, sizeof(int) * (size_t)N);
+    ALLOC(h->d_slot_of_uid, sizeof(int) * K_max);
+    ALLOC(h->d_uid_of_slot, sizeof(int) * K_max);
+    ALLOC(h->d_uid_free, sizeof(int) * K_max);
+    ALLOC(h->d_counts, sizeof(long long) * (K_max + 1));
+    ALLOC(h->d_num, sizeof(double) * (size_t)(K_max + 1) * DP);
+    ALLOC(h->d_S, sizeof(double) * (size_t)(K_max + 1) * SS);
+    ALLOC(h->d_rec, sizeof(double) * (size_t)(K_max + 1) * R);
+    ALLOC(h->d_wbuf, sizeof(double) * (size_t)h->grid * (K_max + 1) * T_SWEEP);
+    ALLOC(h->d_rec_prior, sizeof(double) * R);
+    ALLOC(h->d_ctl, sizeof(Ctl));
+    ALLOC(h->d_err, sizeof(int));
+    ALLOC(h->d_u, sizeof(double) * (size_t)N);
+    ALLOC(h->d_order, sizeof(long long) * (size_t)N);
+    ALLOC(h->d_tmp_ll, sizeof(long long) * (size_t)(N + K_max + 2));
+#undef ALLOC
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+
+    // uploads
+    if (DP == D) {
+        CU(cudaMemcpy(h->dX, X, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice));
+    } else {
+        CU(cudaMemset(h->dX, 0, sizeof(double) * (size_t)N * DP));
+        CU(cudaMemcpy2D(h->dX, sizeof(double) * DP, X, sizeof(double) * D, sizeof(double) * D, (size_t)N,
+                        cudaMemcpyHostToDevice));
+    }
+    if (lgamma_half_tab) {
+        CU(cudaMemcpy(h->d_lgam, lgamma_half_tab, sizeof(double) * (size_t)need, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_logv, log_tab, sizeof(double) * (size_t)need, cudaMemcpyHostToDevice));
+    } else {  // n = [1, 1, 2, ..., v0+N+1]  (gaussian_components.py:120-122), libm instead of SciPy
+        std::vector<double> lg((size_t)need), lv((size_t)need);
+        for (int64_t t = 0; t < need; ++t) {
+            const double n = (t == 0) ? 1.0 : (double)t;
+            lg[t] = lgamma(n / 2.);
+            lv[t] = log(n);
+        }
+        CU(cudaMemcpy(h->d_lgam, lg.data(), sizeof(double) * (size_t)need, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_logv, lv.data(), sizeof(double) * (size_t)need, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(h->d_m0, h->m0.data(), sizeof(double) * DP, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_S0, h->S0p.data(), sizeof(double) * SS, cudaMemcpyHostToDevice));
+    CU(cudaMemset(h->d_err, 0, sizeof(int)));
+    CU(cudaMemset(h->d_z, 0xff, sizeof(int) * (size_t)N));
+    CU(cudaMemset(h->d_counts, 0, sizeof(long long) * (K_max + 1)));
+    CU(cudaMemset(h->d_num, 0, sizeof(double) * (size_t)(K_max + 1) * DP));
+    CU(cudaMemset(h->d_S, 0, sizeof(double) * (size_t)(K_max + 1) * SS));
+    CU(cudaMemset(h->d_rec, 0, sizeof(double) * (size_t)(K_max + 1) * R));
+    {
+        std::vector<int> neg(K_max, -1), fr(K_max);
+        for (int t = 0; t < K_max; ++t) fr[t] = K_max - 1 - t;
+        CU(cudaMemcpy(h->d_slot_of_uid, neg.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_uid_of_slot, neg.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_uid_free, fr.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice));
+        Ctl c;
+        memset(&c, 0, sizeof(c));
+        c.n_free = K_max;
+        c.first = POS_INF;
+        const double one = 1.0;
+        memcpy(&c.margin_bits, &one, 8);
+        CU(cudaMemcpy(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
+    }
+    h->K = 0;
+    // cached_log_prior
+    Params p = make_params(h);
+    if (int rc = h->ops->log_prior(h, p)) { free_all(h); delete h; return rc; }
+    if (int rc = check_dev_err(h, "log_prior")) { free_all(h); delete h; return rc; }
+    *out = h;
+    return 0;
+}
+
+int bgmm_destroy(bgmm_t *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_all(h);
+    delete h;
+    return 0;
+}
+
+int bgmm_set_stream(bgmm_t *h, void *cuda_stream) {
+    if (!h) return fail(BGMM_EINVAL, "handle is NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int bgmm_set_engine(bgmm_t *h, int32_t mode) {
+    if (!h || mode < 0 || mode > 2) return fail(BGMM_EINVAL, "engine mode must be 0, 1 or 2");
+    h->engine = mode;
+    return 0;
+}
+
+int bgmm_seed(bgmm_t *h, uint64_t seed) {
+    if (!h) return fail(BGMM_EINVAL, "handle is NULL");
+    h->seed = seed;
+    h->sweep_index = 0;
+    return 0;
+}
+int64_t bgmm_sweep_index(bgmm_t *h) { return h ? h->sweep_index : -1; }
+
+int bgmm_get_uniforms(bgmm_t *h, int64_t sweep_index, double *out) {
+    if (!h || !out) return fail(BGMM_EINVAL, "NULL argument");
+    CU(cudaSetDevice(h->device));
+    double *tmp = (double *)h->d_tmp_ll;  // N doubles fit in the N long long scratch
+    const int T = 256;
+    k_philox<<<(unsigned)((h->N + T - 1) / T), T, 0, h->stream>>>(tmp, h->N, h->seed, (unsigned long long)sweep_index);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, tmp, sizeof(double) * (size_t)h->N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int bgmm_set_assignments(bgmm_t *h, const int64_t *z) {
+    if (!h || !z) return fail(BGMM_EINVAL, "NULL argument");
+    CU(cudaSetDevice(h->device));
+    const long long N = h->N;
+    const int K_max = h->K_max, DP = h->DP;
+    const int SS = stat_len(DP, h->cov), R = h->ops->rec_len;
+    long long zmax = -1;
+    for (long long i = 0; i < N; ++i) {
+        if (z[i] < -1) return fail(BGMM_EINVAL, "assignments must be -1 or >= 0");
+        zmax = std::max<long long>(zmax, z[i]);
+    }
+    const int K0 = (int)(zmax + 1);
+    if (K0 > K_max) return fail(BGMM_EKMAX, "assignments use more than K_max components");
+    std::vector<long long> start(K0 + 1, 0);
+    for (long long i = 0; i < N; ++i) if (z[i] >= 0) start[z[i] + 1] += 1;
+    for (int k = 0; k < K0; ++k) {
+        // labels must be consecutive (gaussian_components.py:103-105 asserts)
+        if (start[k + 1] == 0) return fail(BGMM_EINVAL, "assignments must be labelled 0..max without gaps");
+    }
+    std::vector<long long> counts(K_max + 1, 0);
+    for (int k = 0; k < K0; ++k) counts[k] = start[k + 1];
+    for (int k = 0; k < K0; ++k) start[k + 1] += start[k];
+    std::vector<long long> idx((size_t)std::max<long long>(N, 1));
+    {
+        std::vector<long long> fill(start.begin(), start.end());
+        for (long long i = 0; i < N; ++i) if (z[i] >= 0) idx[fill[z[i]]++] = i;
+    }
+    std::vector<int> zi((size_t)N);
+    for (long long i = 0; i < N; ++i) zi[i] = (int)z[i];
+    std::vector<int> sl(K_max, -1), fr(K_max, 0);
+    for (int k = 0; k < K0; ++k) sl[k] = k;
+    const int n_free = K_max - K0;
+    for (int t = 0; t < n_free; ++t) fr[t] = K_max - 1 - t;
+
+    cudaStream_t st = h->stream;
+    long long *d_idx = h->d_tmp_ll, *d_start = h->d_tmp_ll + N;
+    CU(cudaMemcpyAsync(d_idx, idx.data(), sizeof(long long) * (size_t)N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_start, start.data(), sizeof(long long) * (K0 + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_z, zi.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_counts, counts.data(), sizeof(long long) * (K_max + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_slot_of_uid, sl.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_uid_of_slot, sl.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_uid_free, fr.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->d_num, 0, sizeof(double) * (size_t)(K_max + 1) * DP, st));
+    CU(cudaMemsetAsync(h->d_S, 0, sizeof(double) * (size_t)(K_max + 1) * SS, st));
+    CU(cudaMemsetAsync(h->d_rec, 0, sizeof(double) * (size_t)(K_max + 1) * R, st));
+    Ctl c;
+    memset(&c, 0, sizeof(c));
+    c.K = K0; c.n_free = n_free; c.first = POS_INF;
+    const double one = 1.0;
+    memcpy(&c.margin_bits, &one, 8);
+    CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
+    Params p = make_params(h);
+    if (K0 > 0) {
+        if (h->cov == BGMM_COV_FULL) k_build_stats<COV_FULL><<<K0, 256, 0, st>>>(p, d_idx, d_start, DP);
+        else k_build_stats<COV_DIAG><<<K0, 256, 0, st>>>(p, d_idx, d_start, DP);
+        CU(cudaGetLastError());
+        if (int rc = h->ops->refactor_all(h, p, K0)) return rc;
+    }
+    CU(cudaStreamSynchronize(st));  // host vectors go out of scope
+    h->K = K0;
+    h->last_gap = 0.0;
+    return check_dev_err(h, "set_assignments");
+}
+
+static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u, double alpha, double power,
+                     bgmm_sweep_stats *out) {
+    if (!(alpha > 0.0)) return fail(BGMM_EINVAL, "alpha must be > 0");
+    if (!(power > 0.0)) return fail(BGMM_EINVAL, "power must be > 0");
+    cudaStream_t st = h->stream;
+    if (!d_u) {
+        const int T = 256;
+        k_philox<<<(unsigned)((h->N + T - 1) / T), T, 0, st>>>(h->d_u, h->N, h->seed, (unsigned long long)h->sweep_index);
+        CU(cudaGetLastError());
+        d_u = h->d_u;
+    }
+    // reset the per-sweep counters (keep K, n_free, barrier words)
+    Ctl c;
+    CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c.moves = c.births = c.deaths = c.evals = c.windows = c.seq_data = c.wasted = 0;
+    const double one = 1.0;
+    memcpy(&c.margin_bits, &one, 8);
+    c.error = 0; c.bar_count = 0; c.pos = 0; c.win = 0; c.first = POS_INF; c.n_dirty = 0;
+    CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
+    Params p = make_params(h);
+    p.order = d_order; p.u = d_u;
+    p.log_alpha = log(alpha); p.power = power;
+    p.init_gap = h->last_gap;
+    CU(cudaEventRecord(h->ev0, st));
+    if (int rc = h->ops->sweep(h, p)) return rc;
+    CU(cudaEventRecord(h->ev1, st));
+    CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->K = c.K;
+    h->sweep_index += 1;
+    h->last_gap = (double)h->N / (double)(c.moves + 1);
+    if (out) {
+        out->K = c.K; out->moves = c.moves; out->births = c.births; out->deaths = c.deaths; out->evals = c.evals;
+        out->windows = c.windows; out->seq_data = c.seq_data; out->wasted = c.wasted;
+        memcpy(&out->min_margin, &c.margin_bits, 8);
+        out->device_ms = ms;
+    }
+    if (c.error == BGMM_EKMAX) return fail(BGMM_EKMAX, "a new component would exceed K_max (the reference raises IndexError)");
+    if (c.error != 0) return fail(c.error, "sweep: non-finite weights or covariance not positive definite");
+    return 0;
+}
+
+int bgmm_sweep_dev(bgmm_t *h, const int64_t *d_order, const double *d_uniforms, double alpha, double power,
+                   bgmm_sweep_stats *out) {
+    if (!h) return fail(BGMM_EINVAL, "handle is NULL");
+    CU(cudaSetDevice(h->device));
+    return run_sweep(h, (const long long *)d_order, d_uniforms, alpha, power, out);
+}
+
+int bgmm_sweep(bgmm_t *h, const int64_t *order, const double *uniforms, double alpha, double power,
+               bgmm_sweep_stats *out) {
+    if (!h) return fail(BGMM_EINVAL, "handle is NULL");
+    CU(cudaSetDevice(h->device));
+    const long long *d_order = nullptr;
+    const double *d_u = nullptr;
+    if (order) {
+        CU(cudaMemcpyAsync(h->d_order, order, sizeof(long long) * (size_t)h->N, cudaMemcpyHostToDevice, h->stream));
+        d_order = h->d_order;
+    }
+    if (uniforms) {
+        CU(cudaMemcpyAsync(h->d_u, uniforms, sizeof(double) * (size_t)h->N, cudaMemcpyHostToDevice, h->stream));
+        d_u = h->d_u;
+    }
+    return run_sweep(h, d_order, d_u, alpha, power, out);
+}
+
+int bgmm_K(bgmm_t *h) { return h ? h->K : -1; }
+
+int bgmm_get_assignments_dev(bgmm_t *h, int64_t *d_out) {
+    if (!h || !d_out) return fail(BGMM_EINVAL, "NULL argument");
+    CU(cudaSetDevice(h->device));
+    const int T = 256;
+    k_relabel<<<(unsigned)((h->N + T - 1) / T), T, 0, h->stream>>>(h->d_z, h->d_slot_of_uid, h->N, (long long *)d_out);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int bgmm_get_state(bgmm_t *h, int64_t *z, int64_t *counts, int32_t *K, double *m_num, double *S_part, double *logdet,
+                   double *inv_covar) {
+    if (!h) return fail(BGMM_EINVAL, "handle is NULL");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int D = h->D, DP = h->DP, K_max = h->K_max, Kl = h->K;
+    const int SS = stat_len(DP, h->cov);
+    const size_t ssr = (h->cov == BGMM_COV_FULL) ? (size_t)D * D : (size_t)D;
+    if (K) *K = Kl;
+    if (z) {
+        if (int rc = bgmm_get_assignments_dev(h, (int64_t *)h->d_tmp_ll)) return rc;
+        CU(cudaMemcpyAsync(z, h->d_tmp_ll, sizeof(long long) * (size_t)h->N, cudaMemcpyDeviceToHost, st));
+    }
+    if (counts) {
+        CU(cudaMemcpyAsync(counts, h->d_counts, sizeof(long long) * K_max, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int k = Kl; k < K_max; ++k) counts[k] = 0;
+    }
+    if (m_num) {
+        std::vector<double> t((size_t)std::max(Kl, 1) * DP);
+        CU(cudaMemcpyAsync(t.data(), h->d_num, sizeof(double) * (size_t)Kl * DP, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        memset(m_num, 0, sizeof(double) * (size_t)K_max * D);
+        for (int k = 0; k < Kl; ++k) for (int a = 0; a < D; ++a) m_num[(size_t)k * D + a] = t[(size_t)k * DP + a];
+    }
+    if (S_part) {
+        std::vector<double> t((size_t)std::max(Kl, 1) * SS);
+        CU(cudaMemcpyAsync(t.data(), h->d_S, sizeof(double) * (size_t)Kl * SS, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        memset(S_part, 0, sizeof(double) * (size_t)K_max * ssr);
+        for (int k = 0; k < Kl; ++k) {
+            if (h->cov == BGMM_COV_FULL) {
+                for (int a = 0; a < D; ++a)
+                    for (int b = 0; b <= a; ++b) {
+                        const double v = t[(size_t)k * SS + row_idx(a, b)];
+                        S_part[(size_t)k * ssr + a * D + b] = v;
+                        S_part[(size_t)k * ssr + b * D + a] = v;
+                    }
+            } else {
+                for (int a = 0; a < D; ++a) S_part[(size_t)k * ssr + a] = t[(size_t)k * SS + a];
+            }
+        }
+    }
+    if (logdet || inv_covar) {
+        double *d_ld = nullptr, *d_inv = nullptr;
+        std::vector<double> ld(std::max(Kl, 1)), iv((size_t)std::max(Kl, 1) * ssr);
+        if (Kl > 0) {
+            CU(cudaMalloc((void **)&d_ld, sizeof(double) * Kl));
+            CU(cudaMalloc((void **)&d_inv, sizeof(double) * (size_t)Kl * ssr));
+            Params p = make_params(h);
+            if (h->cov == BGMM_COV_FULL) k_inv_covar<COV_FULL><<<Kl, 32, sizeof(double) * D * D, st>>>(p, DP, d_ld, d_inv);
+            else k_inv_covar<COV_DIAG><<<Kl, 32, 0, st>>>(p, DP, d_ld, d_inv);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(ld.data(), d_ld, sizeof(double) * Kl, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(iv.data(), d_inv, sizeof(double) * (size_t)Kl * ssr, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            cudaFree(d_ld);
+            cudaFree(d_inv);
+        }
+        if (logdet) {
+            memset(logdet, 0, sizeof(double) * K_max);
+            for (int k = 0; k < Kl; ++k) logdet[k] = ld[k];
+        }
+        if (inv_covar) {
+            memset(inv_covar, 0, sizeof(double) * (size_t)K_max * ssr);
+            memcpy(inv_covar, iv.data(), sizeof(double) * (size_t)Kl * ssr);
+        }
+    }
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bgmm_log_prior(bgmm_t *h, double *out) {
+    if (!h || !out) return fail(BGMM_EINVAL, "NULL argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(out, h->d_log_prior, sizeof(double) * (size_t)h->N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int bgmm_log_post_pred(bgmm_t *h, const int64_t *idx, int64_t n, double *out) {
+    if (!h || (n > 0 && (!idx || !out))) return fail(BGMM_EINVAL, "NULL argument");
+    if (n <= 0 || h->K == 0) return 0;
+    for (int64_t t = 0; t < n; ++t)
+        if (idx[t] < 0 || idx[t] >= h->N) return fail(BGMM_EINVAL, "datum index out of range");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    long long *d_idx = nullptr;
+    double *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_idx, sizeof(long long) * (size_t)n));
+    CU(cudaMalloc((void **)&d_out, sizeof(double) * (size_t)n * h->K));
+    CU(cudaMemcpyAsync(d_idx, idx, sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, st));
+    Params p = make_params(h);
+    int rc = h->ops->lpp(h, p, d_idx, n, h->K, d_out);
+    if (rc == 0) {
+        cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n * h->K, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+    }
+    cudaFree(d_idx);
+    cudaFree(d_out);
+    return rc;
+}
+
+int bgmm_log_marg_k(bgmm_t *h, double *out) {
+    if (!h || !out) return fail(BGMM_EINVAL, "NULL argument");
+    if (h->K == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    double *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_out, sizeof(double) * h->K));
+    Params p = make_params(h);
+    if (h->cov == BGMM_COV_FULL)
+        k_log_marg_k<COV_FULL><<<h->K, 32, sizeof(double) * (packed_len(h->D) + 2), st>>>(p, h->DP, h->logdet_S0, d_out);
+    else
+        k_log_marg_k<COV_DIAG><<<h->K, 32, 16, st>>>(p, h->DP, h->logdet_S0, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out, sizeof(double) * h->K, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_out);
+    return 0;
+}
+
+int bgmm_log_marg(bgmm_t *h, double alpha, double *out) {
+    if (!h || !out) return fail(BGMM_EINVAL, "NULL argument");
+    const int K = h->K;
+    std::vector<double> lk(std::max(K, 1));
+    std::vector<long long> cnt(h->K_max);
+    if (int rc = bgmm_log_marg_k(h, lk.data())) return rc;
+    CU(cudaMemcpy(cnt.data(), h->d_counts, sizeof(long long) * h->K_max, cudaMemcpyDeviceToHost));
+    // igmm.py:199-215
+    double facts = 0.0;
+    long long tot = 0;
+    for (int k = 0; k < K; ++k) {
+        if (cnt[k] != 0) facts += lgamma((double)cnt[k]);
+        tot += cnt[k];
+    }
+    const double lpz = (K - 1) * log(alpha) + lgamma(alpha) - lgamma((double)tot + alpha) + facts;
+    double lpx = 0.0;
+    for (int k = 0; k < K; ++k) lpx += lk[k];
+    *out = lpz + lpx;
+    return 0;
+}
+
+static int item_op(bgmm_handle *h, int op, long long i, int k) {
+    if (!h) return fail(BGMM_EINVAL, "handle is NULL");
+    if (i < 0 || i >= h->N) return fail(BGMM_EINVAL, "datum index out of range");
+    CU(cudaSetDevice(h->device));
+    Params p = make_params(h);
+    if (int rc = h->ops->item_op(h, p, op, i, k)) return rc;
+    Ctl c;
+    CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->K = c.K;
+    if (c.error) {
+        const int e = c.error;
+        c.error = 0;
+        cudaMemcpy(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice);
+        return fail(e, e == BGMM_EKMAX ? "K_max overflow" : (e == BGMM_EINVAL ? "invalid component index" : "numeric failure"));
+    }
+    return 0;
+}
+int bgmm_add_item(bgmm_t *h, int64_t i, int32_t k) { return item_op(h, 1, i, k); }
+int bgmm_del_item(bgmm_t *h, int64_t i) { return item_op(h, 0, i, 0); }
+
+}  // extern "C"
