@@ -130,6 +130,9 @@ int bgmm_log_marg(bgmm_t *h, double alpha, double *out);
 /* replaces: add_item(i,k) (gaussian_components.py:154-169) and del_item(i) (:171-186, incl. del_component :188-205) */
 int bgmm_add_item(bgmm_t *h, int64_t i, int32_t k);
 int bgmm_del_item(bgmm_t *h, int64_t i);
+/* replaces: restore_component_from_stats(k, ...) (gaussian_components.py:144-152): overwrite the sufficient statistics
+ * of live component k (m_num: D, S_part: D*D full | D diag, count) -- logdet/inv are re-derived from them. */
+int bgmm_set_component_stats(bgmm_t *h, int32_t k, const double *m_num, const double *S_part, int64_t count);
 
 /*
  * replaces: the stream of random.random() calls made by utils.draw (utils/utils.py:15).  `state` is the 625-word

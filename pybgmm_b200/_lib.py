@@ -15,6 +15,7 @@ BGMM_OK, BGMM_EINVAL, BGMM_ENODEV, BGMM_EKMAX, BGMM_ENUMERIC, BGMM_ENOMEM = 0, -
 COV_FULL, COV_DIAG = 0, 1
 
 EXPORTS = (
+    "bgmm_set_component_stats",
     "bgmm_version", "bgmm_last_error", "bgmm_device_count", "bgmm_create", "bgmm_destroy", "bgmm_set_stream",
     "bgmm_set_assignments", "bgmm_sweep", "bgmm_sweep_dev", "bgmm_set_engine", "bgmm_seed", "bgmm_get_uniforms",
     "bgmm_sweep_index", "bgmm_get_state", "bgmm_get_assignments_dev", "bgmm_K", "bgmm_log_prior",
@@ -74,6 +75,7 @@ def lib():
     L.bgmm_log_marg.argtypes = [vp, C.c_double, dp]
     L.bgmm_add_item.argtypes = [vp, C.c_int64, C.c_int32]
     L.bgmm_del_item.argtypes = [vp, C.c_int64]
+    L.bgmm_set_component_stats.argtypes = [vp, C.c_int32, dp, dp, C.c_int64]
     L.bgmm_mt19937_fill.argtypes = [C.POINTER(C.c_uint32), dp, C.c_int64]
     _LIB = L
     return L

@@ -496,7 +496,7 @@ int bgmm_set_assignments(bgmm_t *h, const int64_t *z) {
         if (h->cov == BGMM_COV_FULL) k_build_stats<COV_FULL><<<K0, 256, 0, st>>>(p, d_idx, d_start, DP);
         else k_build_stats<COV_DIAG><<<K0, 256, 0, st>>>(p, d_idx, d_start, DP);
         CU(cudaGetLastError());
-        if (int rc = h->ops->refactor_all(h, p, K0)) return rc;
+        if (int rc = h->ops->refactor_all(h, p, 0, K0)) return rc;
     }
     CU(cudaStreamSynchronize(st));  // host vectors go out of scope
     h->K = K0;
@@ -744,6 +744,29 @@ static int item_op(bgmm_handle *h, int op, long long i, int k) {
         return fail(e, e == BGMM_EKMAX ? "K_max overflow" : (e == BGMM_EINVAL ? "invalid component index" : "numeric failure"));
     }
     return 0;
+}
+int bgmm_set_component_stats(bgmm_t *h, int32_t k, const double *m_num, const double *S_part, int64_t count) {
+    if (!h || !m_num || !S_part) return fail(BGMM_EINVAL, "NULL argument");
+    if (k < 0 || k >= h->K) return fail(BGMM_EINVAL, "component index out of range");
+    if (count < 1) return fail(BGMM_EINVAL, "count must be >= 1");
+    CU(cudaSetDevice(h->device));
+    const int D = h->D, DP = h->DP, SS = stat_len(DP, h->cov);
+    std::vector<double> num(DP, 0.0), S(SS, 0.0);
+    for (int a = 0; a < D; ++a) num[a] = m_num[a];
+    if (h->cov == BGMM_COV_FULL) {
+        for (int a = 0; a < D; ++a) for (int b = 0; b <= a; ++b) S[row_idx(a, b)] = S_part[a * D + b];
+    } else {
+        for (int a = 0; a < D; ++a) S[a] = S_part[a];
+    }
+    const long long c = count;
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(h->d_num + (size_t)k * DP, num.data(), sizeof(double) * DP, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_S + (size_t)k * SS, S.data(), sizeof(double) * SS, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_counts + k, &c, sizeof(long long), cudaMemcpyHostToDevice, st));
+    Params p = make_params(h);
+    if (int rc = h->ops->refactor_all(h, p, k, 1)) return rc;
+    CU(cudaStreamSynchronize(st));
+    return check_dev_err(h, "set_component_stats");
 }
 int bgmm_add_item(bgmm_t *h, int64_t i, int32_t k) { return item_op(h, 1, i, k); }
 int bgmm_del_item(bgmm_t *h, int64_t i) { return item_op(h, 0, i, 0); }

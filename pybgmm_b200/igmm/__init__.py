@@ -1,0 +1,6 @@
+"""Infinite Gaussian mixture samplers on the B200 engine (mirror of pybgmm/igmm/__init__.py)."""
+from .igmm import IGMM
+from .crpmm import CRPMM
+from .pcrpmm import PCRPMM
+
+__all__ = ["IGMM", "CRPMM", "PCRPMM"]
