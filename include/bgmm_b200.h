@@ -51,6 +51,9 @@ typedef struct {
     int64_t wasted;     /* speculative datum evaluations discarded and redone (engine diagnostic)     */
     double min_margin;  /* min distance of a uniform to the CDF boundary it was compared with         */
     double device_ms;   /* CUDA-event time of the sweep kernel(s), summed                             */
+    int64_t explicit_evals; /* own-component weights rebuilt exactly from the statistics (engine diagnostic)  */
+    int64_t refreshes;      /* records rebuilt from the statistics for drift control (engine diagnostic)      */
+    int64_t generic_from;   /* scan position the generic engine took over at, or -1 (engine diagnostic)       */
 } bgmm_sweep_stats;
 
 const char *bgmm_version(void);
@@ -97,7 +100,8 @@ int bgmm_sweep(bgmm_t *h, const int64_t *order, const double *uniforms, double a
 /* Same, with `d_order` / `d_uniforms` already resident in device memory (either may be NULL as above). */
 int bgmm_sweep_dev(bgmm_t *h, const int64_t *d_order, const double *d_uniforms, double alpha, double power,
                    bgmm_sweep_stats *out);
-/* Engine policy: 0 = adaptive (default), 1 = always the sequential per-datum path, 2 = always speculative windows. */
+/* Engine policy: 0 = adaptive (default), 1 = always the sequential per-datum path, 2 = always speculative windows;
+ * 3..5 = the same three policies on the generic engine (any D, any K_max) instead of the shared-memory-resident one. */
 int bgmm_set_engine(bgmm_t *h, int32_t mode);
 
 /* Philox stream used when uniforms == NULL: seed it, and replay the stream of a given sweep index on the host

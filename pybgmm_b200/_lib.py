@@ -26,7 +26,8 @@ EXPORTS = (
 class SweepStats(C.Structure):
     _fields_ = [("K", C.c_int64), ("moves", C.c_int64), ("births", C.c_int64), ("deaths", C.c_int64),
                 ("evals", C.c_int64), ("windows", C.c_int64), ("seq_data", C.c_int64), ("wasted", C.c_int64),
-                ("min_margin", C.c_double), ("device_ms", C.c_double)]
+                ("min_margin", C.c_double), ("device_ms", C.c_double), ("explicit_evals", C.c_int64),
+                ("refreshes", C.c_int64), ("generic_from", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -161,7 +162,8 @@ class Chain(object):
         _check(lib().bgmm_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
     def set_engine(self, mode):
-        _check(lib().bgmm_set_engine(self._h, {"adaptive": 0, "sequential": 1, "windows": 2}.get(mode, mode)))
+        _check(lib().bgmm_set_engine(self._h, {"adaptive": 0, "sequential": 1, "windows": 2, "generic": 3, "generic-sequential": 4,
+                                                 "generic-windows": 5}.get(mode, mode)))
 
     def seed(self, seed):
         _check(lib().bgmm_seed(self._h, int(seed)))

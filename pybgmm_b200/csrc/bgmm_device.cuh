@@ -63,6 +63,9 @@ struct Ctl {
     long long moves, births, deaths, evals, windows, seq_data, wasted;
     unsigned long long margin_bits;
     double gap;         // running estimate of the number of data between two movers
+    // fast engine (bgmm_fast.cuh)
+    unsigned long long first3[3];  // per-round atomicMin targets (round r uses slot r % 3)
+    long long explicit_evals, refreshes;
 };
 
 struct Params {
@@ -75,6 +78,7 @@ struct Params {
     const double *u;          // N uniforms in scan order
     // mutable state
     int *z_uid;               // N
+    int *z_out;               // N: labels written by the fast engine (z_uid stays the sweep's read-only input)
     int *slot_of_uid;         // K_max
     int *uid_of_slot;         // K_max
     int *uid_free;            // K_max (stack)
@@ -96,6 +100,11 @@ struct Params {
     double log_pi;
     int engine;               // 0 adaptive, 1 sequential, 2 windows
     double init_gap;
+    long long start_pos;      // scan position the sweep (re)starts at
+    // fast engine (bgmm_fast.cuh): element-major records rec[e * KS + k] and the prior's record
+    double *recB;
+    double *recB_prior;
+    int KS, Kcap;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -205,7 +205,7 @@ static void free_all(bgmm_handle *h) {
     cudaFree(h->d_S0); cudaFree(h->d_z); cudaFree(h->d_slot_of_uid); cudaFree(h->d_uid_of_slot); cudaFree(h->d_uid_free);
     cudaFree(h->d_counts); cudaFree(h->d_num); cudaFree(h->d_S); cudaFree(h->d_rec); cudaFree(h->d_wbuf);
     cudaFree(h->d_rec_prior); cudaFree(h->d_ctl); cudaFree(h->d_err); cudaFree(h->d_u); cudaFree(h->d_order);
-    cudaFree(h->d_tmp_ll);
+    cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
 }
@@ -309,7 +309,9 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
     h->Kc = (int)kc;
     h->smem_bytes = fixed + (size_t)h->Kc * R * sizeof(double) + 32;
     h->smem_item = fixed + 32;
+    h->smem_optin = smem_max;
     if (int rc = prep(h)) { delete h; return rc; }
+    if (int rc = h->ops->fast_setup(h)) { free_all(h); delete h; return rc; }
 
 #define ALLOC(ptr, bytes)                                                                             \
     do {                                                                                              \
@@ -383,6 +385,7 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
         memset(&c, 0, sizeof(c));
         c.n_free = K_max;
         c.first = POS_INF;
+        c.first3[0] = c.first3[1] = c.first3[2] = (unsigned long long)POS_INF;
         const double one = 1.0;
         memcpy(&c.margin_bits, &one, 8);
         CU(cudaMemcpy(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
@@ -414,7 +417,7 @@ int bgmm_set_stream(bgmm_t *h, void *cuda_stream) {
 }
 
 int bgmm_set_engine(bgmm_t *h, int32_t mode) {
-    if (!h || mode < 0 || mode > 2) return fail(BGMM_EINVAL, "engine mode must be 0, 1 or 2");
+    if (!h || mode < 0 || mode > 5) return fail(BGMM_EINVAL, "engine mode must be in 0..5");
     h->engine = mode;
     return 0;
 }
@@ -488,6 +491,7 @@ int bgmm_set_assignments(bgmm_t *h, const int64_t *z) {
     Ctl c;
     memset(&c, 0, sizeof(c));
     c.K = K0; c.n_free = n_free; c.first = POS_INF;
+    c.first3[0] = c.first3[1] = c.first3[2] = (unsigned long long)POS_INF;
     const double one = 1.0;
     memcpy(&c.margin_bits, &one, 8);
     CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
@@ -520,16 +524,43 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     c.moves = c.births = c.deaths = c.evals = c.windows = c.seq_data = c.wasted = 0;
+    c.explicit_evals = c.refreshes = 0;
     const double one = 1.0;
     memcpy(&c.margin_bits, &one, 8);
     c.error = 0; c.bar_count = 0; c.pos = 0; c.win = 0; c.first = POS_INF; c.n_dirty = 0;
+    c.first3[0] = c.first3[1] = c.first3[2] = (unsigned long long)POS_INF;
     CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
     Params p = make_params(h);
     p.order = d_order; p.u = d_u;
     p.log_alpha = log(alpha); p.power = power;
     p.init_gap = h->last_gap;
+    long long generic_from = -1;
     CU(cudaEventRecord(h->ev0, st));
-    if (int rc = h->ops->sweep(h, p)) return rc;
+    // engine 0..2: the replicated-state-machine engine (bgmm_fast.cuh) where it applies; 3..5: the generic engine
+    bool fast = h->fast_ok && h->engine < 3 && c.K <= h->Kcap;
+    if (fast) {
+        // the replicas read the labels as they were at the start of the sweep; CTA 0 writes the other copy
+        CU(cudaMemcpyAsync(h->d_z2, h->d_z, sizeof(int) * (size_t)h->N, cudaMemcpyDeviceToDevice, st));
+        if (int rc = h->ops->fast_prep(h, p, c.K)) return rc;
+        if (int rc = h->ops->fast_sweep(h, p)) return rc;
+        std::swap(h->d_z, h->d_z2);
+        p.z_uid = h->d_z; p.z_out = h->d_z2;
+        CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        // the generic engine's (Cholesky) records, used by the auxiliary entry points, follow from the statistics
+        if (c.K > 0)
+            if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
+        if (c.error == fast::E_NEED_GENERIC) {  // more live components than fit in shared memory: continue generically
+            generic_from = c.pos;
+            c.error = 0; c.bar_count = 0;
+            CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
+            fast = false;
+        }
+    }
+    if (!fast) {
+        p.start_pos = generic_from < 0 ? 0 : generic_from;
+        if (int rc = h->ops->sweep(h, p)) return rc;
+    }
     CU(cudaEventRecord(h->ev1, st));
     CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -543,6 +574,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         out->windows = c.windows; out->seq_data = c.seq_data; out->wasted = c.wasted;
         memcpy(&out->min_margin, &c.margin_bits, 8);
         out->device_ms = ms;
+        out->explicit_evals = c.explicit_evals; out->refreshes = c.refreshes; out->generic_from = generic_from;
     }
     if (c.error == BGMM_EKMAX) return fail(BGMM_EKMAX, "a new component would exceed K_max (the reference raises IndexError)");
     if (c.error != 0) return fail(c.error, "sweep: non-finite weights or covariance not positive definite");

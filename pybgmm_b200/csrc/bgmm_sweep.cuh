@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(T_SWEEP, 1) k_sweep(const Params p) {
             __stcg(p.rec + (size_t)k * R + SO + SC_LC, log_count(n, p.power));
         }
         if (tid == 0) {
-            __stcg(&ctl->pos, 0LL);
+            __stcg(&ctl->pos, p.start_pos);
             __stcg(&ctl->first, POS_INF);
             __stcg(&ctl->n_dirty, 0);
             __stcg(&ctl->gap, p.init_gap);
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(T_SWEEP, 1) k_sweep(const Params p) {
             if (p.engine == 2 || (p.engine == 0 && p.init_gap >= SEQ_GAP)) {
                 const long long wmax = 4LL * gridDim.x * blockDim.x;
                 w = (long long)fmin(fmax(2.0 * p.init_gap, (double)WIN_MIN), (double)wmax);
-                if (w > p.N) w = p.N;
+                if (w > p.N - p.start_pos) w = p.N - p.start_pos;
             }
             __stcg(&ctl->win, w);
         }

@@ -145,3 +145,63 @@ def test_philox_stream_replay(gpu_lib):
         orc.sweep(u, 1.0)
         ch.sweep(1.0)
         np.testing.assert_array_equal(ch.assignments(), orc.assignments)
+
+
+@pytest.mark.parametrize("engine", ["generic", "generic-sequential", "generic-windows"])
+def test_generic_engine_matches_oracle(gpu_lib, engine):
+    """The generic (any D / any K_max) engine stays covered now that D <= 16 full covariance defaults to the
+    shared-memory-resident engine."""
+    N, D, K_true, sweeps = 1200, 4, 6, 4
+    X, orc, ch = _pair(gpu_lib, N, D, K_true, "full", K_init=K_true)
+    ch.set_engine(engine)
+    random.seed(7)
+    for s in range(sweeps):
+        u = np.array([random.random() for _ in range(N)])
+        so = orc.sweep(u, 1.0)
+        sg = ch.sweep(1.0, 1.0, None, u)
+        assert (sg.K, sg.moves, sg.births, sg.deaths, sg.evals) == (so.K_end, so.moves, so.births, so.deaths, so.evals), s
+        np.testing.assert_array_equal(ch.assignments(), orc.assignments)
+    _assert_state_equal(orc, ch)
+
+
+def test_resident_capacity_overflow_hands_over_to_generic(gpu_lib):
+    """More live components than the resident engine holds in shared memory: the sweep is continued by the generic
+    engine from the scan position of the offending birth (bgmm_sweep_stats.generic_from), same chain as the oracle."""
+    N, D = 700, 2
+    X, z_true = make_data(N, D, 40, 1, mean_scale=60.0)
+    m_0, k_0, v_0, S_0 = make_prior(D)
+    K_max = 600
+    z0 = O.init_assignments(N, "rand", 150)
+    orc = O.Oracle(X, m_0, k_0, v_0, S_0, K_max=K_max)
+    orc.set_assignments(z0)
+    ch = gpu_lib.Chain(X, m_0, k_0, v_0, S_0, K_max)
+    ch.set_assignments(z0)
+    rng = np.random.RandomState(3)
+    handed_over = []
+    for s in range(4):
+        u = rng.random_sample(N)
+        so = orc.sweep(u, 1e4)
+        sg = ch.sweep(1e4, 1.0, None, u)
+        handed_over.append(sg.generic_from)
+        assert (sg.K, sg.moves, sg.births, sg.deaths, sg.evals) == (so.K_end, so.moves, so.births, so.deaths, so.evals), s
+        np.testing.assert_array_equal(ch.assignments(), orc.assignments)
+    assert handed_over[0] > 0, "sweep 0 should cross the resident capacity mid-sweep"
+    _assert_state_equal(orc, ch)
+
+
+def test_long_chain_drift_control(gpu_lib):
+    """Many rank-one record updates per component (records are rebuilt from the bit-exact statistics every
+    REFRESH_EVERY updates): the chain still follows the oracle and the statistics stay bit-identical."""
+    N, D, K_true = 6000, 8, 3
+    X, orc, ch = _pair(gpu_lib, N, D, K_true, "full", K_init=3, K_max=32)
+    rng = np.random.RandomState(11)
+    refreshes = 0
+    for s in range(3):
+        u = rng.random_sample(N)
+        so = orc.sweep(u, 1.0)
+        sg = ch.sweep(1.0, 1.0, None, u)
+        refreshes += sg.refreshes
+        assert (sg.K, sg.moves, sg.births, sg.deaths, sg.evals) == (so.K_end, so.moves, so.births, so.deaths, so.evals), s
+        np.testing.assert_array_equal(ch.assignments(), orc.assignments)
+    assert refreshes > 0
+    _assert_state_equal(orc, ch)
