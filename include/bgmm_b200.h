@@ -54,6 +54,7 @@ typedef struct {
     int64_t explicit_evals; /* own-component weights rebuilt exactly from the statistics (engine diagnostic)  */
     int64_t refreshes;      /* records rebuilt from the statistics for drift control (engine diagnostic)      */
     int64_t generic_from;   /* scan position the generic engine took over at, or -1 (engine diagnostic)       */
+    int64_t phase_cycles[16]; /* SM cycles CTA 0 spent per engine phase in the last sweep (engine diagnostic)   */
 } bgmm_sweep_stats;
 
 const char *bgmm_version(void);

@@ -27,10 +27,17 @@ class SweepStats(C.Structure):
     _fields_ = [("K", C.c_int64), ("moves", C.c_int64), ("births", C.c_int64), ("deaths", C.c_int64),
                 ("evals", C.c_int64), ("windows", C.c_int64), ("seq_data", C.c_int64), ("wasted", C.c_int64),
                 ("min_margin", C.c_double), ("device_ms", C.c_double), ("explicit_evals", C.c_int64),
-                ("refreshes", C.c_int64), ("generic_from", C.c_int64)]
+                ("refreshes", C.c_int64), ("generic_from", C.c_int64), ("phase_cycles", C.c_int64 * 16)]
+
+    PHASES = ("stage", "head", "eval", "draw", "update", "scalars", "wineval", "barrier", "rare", "steps", "moves",
+              "rounds")
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "phase_cycles"}
+        return d
+
+    def phases(self):
+        return dict(zip(self.PHASES, list(self.phase_cycles)))
 
 
 class BgmmError(RuntimeError):

@@ -66,6 +66,7 @@ struct Ctl {
     // fast engine (bgmm_fast.cuh)
     unsigned long long first3[3];  // per-round atomicMin targets (round r uses slot r % 3)
     long long explicit_evals, refreshes;
+    long long prof[16];            // phase clocks of CTA 0 (cycles), see bgmm_fast.cuh
 };
 
 struct Params {
@@ -104,6 +105,8 @@ struct Params {
     // fast engine (bgmm_fast.cuh): element-major records rec[e * KS + k] and the prior's record
     double *recB;
     double *recB_prior;
+    double *mvbuf;            // per evaluator warp: the inputs of the candidate it published
+    double *ntab;             // count table: 8 doubles per count n = 0..N (bgmm_fast.cuh NT_*)
     int KS, Kcap;
 };
 

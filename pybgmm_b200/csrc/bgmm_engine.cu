@@ -205,7 +205,7 @@ static void free_all(bgmm_handle *h) {
     cudaFree(h->d_S0); cudaFree(h->d_z); cudaFree(h->d_slot_of_uid); cudaFree(h->d_uid_of_slot); cudaFree(h->d_uid_free);
     cudaFree(h->d_counts); cudaFree(h->d_num); cudaFree(h->d_S); cudaFree(h->d_rec); cudaFree(h->d_wbuf);
     cudaFree(h->d_rec_prior); cudaFree(h->d_ctl); cudaFree(h->d_err); cudaFree(h->d_u); cudaFree(h->d_order);
-    cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2);
+    cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf); cudaFree(h->d_ntab);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
 }
@@ -525,6 +525,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     CU(cudaStreamSynchronize(st));
     c.moves = c.births = c.deaths = c.evals = c.windows = c.seq_data = c.wasted = 0;
     c.explicit_evals = c.refreshes = 0;
+    memset(c.prof, 0, sizeof(c.prof));
     const double one = 1.0;
     memcpy(&c.margin_bits, &one, 8);
     c.error = 0; c.bar_count = 0; c.pos = 0; c.win = 0; c.first = POS_INF; c.n_dirty = 0;
@@ -575,6 +576,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         memcpy(&out->min_margin, &c.margin_bits, 8);
         out->device_ms = ms;
         out->explicit_evals = c.explicit_evals; out->refreshes = c.refreshes; out->generic_from = generic_from;
+        for (int t = 0; t < 16; ++t) out->phase_cycles[t] = c.prof[t];
     }
     if (c.error == BGMM_EKMAX) return fail(BGMM_EKMAX, "a new component would exceed K_max (the reference raises IndexError)");
     if (c.error != 0) return fail(c.error, "sweep: non-finite weights or covariance not positive definite");

@@ -5,7 +5,7 @@
 //
 // Execution model (DESIGN.md "Engine"): a REPLICATED STATE MACHINE.  Every CTA of a cooperative grid
 // (one per SM) keeps the evaluation records of all live components in its own shared memory and applies
-// every state change itself, with identical arithmetic, so the replicas never need to exchange records.
+// every state change itself, with identical arithmetic, so the replicas never exchange records.
 //   * evaluation record of component k (element-major in shared memory, rec[e * KS + k]):
 //       B = S_N^-1 (packed lower triangle), the mean m_N, and the scalars of the Student-t log pdf.
 //     A datum joining / leaving a component is a rank-one change of S_N (gaussian_components.py:161-166,
@@ -13,13 +13,15 @@
 //     records are rebuilt from the bit-exact sufficient statistics at the start of every sweep and after
 //     REFRESH_EVERY rank-one updates of a component (drift control).
 //   * window round: the CTAs split a window of upcoming scan positions (a warp per datum, lanes over
-//     components), each datum is evaluated against the current records; a datum whose draw keeps it where
+//     components); each datum is evaluated against the current records.  A datum whose draw keeps it where
 //     it is leaves the state untouched (the reference's restore path, crpmm.py:82-85), so every "stay"
 //     in front of the first datum that does anything else is exactly the sequential chain's decision.
-//     One atomicMin + ONE grid barrier publish that first position; every CTA then resolves it itself.
+//     One atomicMin + ONE grid barrier publish that first position (and the warp that holds its inputs);
+//     every CTA then resolves it itself.  Warps keep the inputs of the datum they own across rounds.
 //   * sequential batch: when movers are dense, every CTA walks the scan datum by datum (no barriers).
-//   * CTA 0 is the only writer of global state: labels, the bit-exact statistics (same operation order
-//     as the reference: one rounded multiply and one rounded add per element), counters.
+//   * CTA 0 is the only writer of global state: labels (into the sweep's output copy), the bit-exact
+//     statistics (same operation order as the reference: one rounded multiply and one rounded add per
+//     element), counters.  Replicas read mutable global state only between two grid barriers.
 #pragma once
 #include "bgmm_sweep.cuh"
 
@@ -28,34 +30,61 @@ namespace fast {
 
 constexpr int TF = 512;               // threads per CTA
 constexpr int NWARP = TF / 32;
-constexpr int NSC = 16;               // scalars per record
 constexpr int SEQ_BATCH = 16;         // data staged per sequential batch
 constexpr int REFRESH_EVERY = 1024;   // rank-one updates of a record before it is rebuilt from the statistics
 constexpr int NB_MAX = 6;             // weights per lane in the draw: supports K + 1 <= 192
 constexpr int E_NEED_GENERIC = 1;     // internal: a birth would exceed the resident capacity -> generic engine
 constexpr double GAP_TO_WIN = 6.0, GAP_TO_SEQ = 3.0;
 constexpr int WIN_PASSES_MAX = 8;
+constexpr int MV_EXTRA = 4;           // mover slot: x[DP], u, log prior, i, uid
+// phase clocks (CTA 0, thread 0; cycles): reported through bgmm_sweep_stats.phase_cycles
+enum { PH_STAGE = 0, PH_HEAD, PH_EVAL, PH_DRAW, PH_UPDATE, PH_SCALARS, PH_WINEVAL, PH_BARRIER, PH_RARE, PH_STEPS, PH_MOVES,
+       PH_ROUNDS, PH_COUNT = 16 };
+#define F_PROF(slot)                                                  \
+    do {                                                              \
+        if (threadIdx.x == 0 && blockIdx.x == 0) {                    \
+            const long long t_ = clock64();                           \
+            s.sh->prof[slot] += t_ - s.sh->prof_last;                 \
+            s.sh->prof_last = t_;                                     \
+        }                                                             \
+    } while (0)
 
+// Everything in a record that depends on the component's count n alone comes from the count table
+// Params::ntab (8 doubles per n, built once per chain / per power by k_fast_ntab):
+//   NT_CN    LC(n) + TC(n) - D/2 LF(n), with
+//              TC  Student-t constant of nu = v0 + n - D + 1 (gaussian_components.py:237-249 without logdet)
+//              LF  log f(n), f = (kappa + 1) / (kappa nu)                      (:324-329)
+//              LC  log count prior of n (crpmm.py:70 / pcrpmm.py:107)
+//   NT_G     kappa / (kappa + 1) = 1 / (f nu)
+//   NT_H     (nu + D) / 2
+//   NT_BETA  kappa / (kappa - 1)
+//   NT_RK    1 / kappa
+enum { NT_CN = 0, NT_G, NT_H, NT_BETA, NT_RK, NT_W = 8 };
 // record scalars
 enum {
     F_N = 0,   // count n (as double)
     F_LDS,     // log|S_N|
-    F_TC,      // Student-t constant of nu = v0 + n - D + 1 (gaussian_components.py:237-249 without logdet)
-    F_LF,      // log f(n), f = (kappa + 1) / (kappa nu)   (:324-329)
-    F_LC,      // log count prior of n (crpmm.py:70 / pcrpmm.py:107)
-    F_TCM, F_LFM, F_LCM,  // the same three for n - 1 (the datum's own component with the datum removed)
-    F_CW,      // LC + TC - (D LF + LDS) / 2
-    F_G,       // kappa / (kappa + 1) = 1 / (f nu)
-    F_H,       // (nu + D) / 2
-    F_BETA,    // kappa / (kappa - 1)
-    F_CWO,     // LCM + TCM - (D LFM + LDS) / 2
-    F_HO,      // (nu - 1 + D) / 2 - 1 / 2
     F_CNT,     // rank-one updates since the record was rebuilt
-    F_SPARE
+    F_CW,      // CN(n) - LDS / 2
+    F_G, F_H, F_BETA,
+    F_CWO,     // CN(n - 1) - LDS / 2   (the datum's own component without the datum)
+    NSC = 8
+};
+
+template <int DP> struct Lay {
+    static constexpr int PP = DP * (DP + 1) / 2;
+    static constexpr int MU = PP;
+    static constexpr int SC = PP + DP;
+    static constexpr int R = PP + DP + NSC;
+    static constexpr int NS = PP + DP;  // statistics per component: S (packed) then num
+    // compile-time record stride (odd: conflict-free column writes) and resident capacity
+    static constexpr int KS = (DP == 16) ? 145 : 191;
+    static constexpr int KCAP = KS - 1;
+    static constexpr int WS = (KS + 1 + 3) & ~3;
 };
 
 // grid barrier with a watchdog: replicas that stopped agreeing would otherwise spin forever
-__device__ __forceinline__ void f_grid_barrier(Ctl *c) {
+static __device__ __noinline__ void f_grid_barrier(Ctl *c) {
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int gen = ld_acquire_u32(&c->bar_gen);
@@ -68,7 +97,6 @@ __device__ __forceinline__ void f_grid_barrier(Ctl *c) {
         } else {
             const long long t0 = clock64();
             while (ld_acquire_u32(&c->bar_gen) == gen) {
-                __nanosleep(20);
                 if (clock64() - t0 > 8000000000LL) __trap();
             }
         }
@@ -76,14 +104,6 @@ __device__ __forceinline__ void f_grid_barrier(Ctl *c) {
     }
     __syncthreads();
 }
-
-template <int DP> struct Lay {
-    static constexpr int PP = DP * (DP + 1) / 2;
-    static constexpr int MU = PP;
-    static constexpr int SC = PP + DP;
-    static constexpr int R = PP + DP + NSC;
-    static constexpr int NS = PP + DP;  // statistics per component: S (packed) then num
-};
 
 struct FSh {
     // replicated chain state
@@ -93,43 +113,41 @@ struct FSh {
     long long moves, births, deaths, evals, windows, seq_data, wasted, explicit_evals, refreshes;
     unsigned long long margin_bits;
     // datum being resolved
-    long long i;
-    int uid, k_old, k_new, died, need_explicit, explicit_done, refresh_a, refresh_b;
-    double n_old, u, lp, margin;
-    // update scratch
-    double fresh[2][3];   // [a|b][TC, LF, LC]
-    double lds_new[2], n_new[2];
-    int upd_a, upd_b, birth;
+    int k_new, need_explicit, explicit_done, refresh_a, refresh_b;
+    // record version: bumped by every change of the records; the change from ver - 1 to ver touched only the
+    // components dirty_a / dirty_b (-1: none) unless dirty_all
+    int ver, dirty_a, dirty_b, dirty_all;
     unsigned int round;
     unsigned long long mbar;
+    long long prof[PH_COUNT], prof_last;
 };
 
 template <int DP> struct FSmem {
     double *rec;      // R * KS
     double *prior;    // R
     double *tmprec;   // R  (exact record of the datum's own component with the datum removed)
-    double *wrow;     // NWARP * WS
+    double *ew;       // (NWARP + 1) * WS   (per warp: exp(weight - reference) of the K + 1 choices; last row: f_step)
+    double *xw;       // NWARP * DP   (per warp: the datum it owns in the window)
     double *xb;       // SEQ_BATCH * DP
     double *ub, *lpb; // SEQ_BATCH
     long long *ib;    // SEQ_BATCH
     int *uidb;        // SEQ_BATCH
     double *dv;       // 2 * DP   (d of the two updated components)
     double *vv;       // 2 * DP   (v = B d)
+    double *nt;       // 2 * 2 * NT_W  (count-table rows n2 - 1, n2 of the two updated components)
     double *A;        // PP       (exact refactor scratch)
     double *W;        // DP * DP
     double *mm;       // DP
     int *slot_of_uid, *uid_of_slot, *uid_free;  // K_max each
     unsigned short *rc;  // PP: (a << 8) | b of packed element e
     FSh *sh;
-    int WS;
 };
 
-__host__ __device__ inline int fast_ws(int KS) { return (KS + 1 + 3) & ~3; }
-
-template <int DP> __host__ __device__ inline size_t fast_smem_bytes(int KS, int K_max) {
+template <int DP> __host__ __device__ inline size_t fast_smem_bytes(int K_max) {
     using Ly = Lay<DP>;
-    size_t d = (size_t)Ly::R * KS + 2 * (size_t)Ly::R + (size_t)NWARP * fast_ws(KS) + (size_t)SEQ_BATCH * DP +
-               2 * SEQ_BATCH + SEQ_BATCH /*ib*/ + SEQ_BATCH / 2 /*uidb*/ + 4 * DP + Ly::PP + DP * DP + DP;
+    size_t d = (size_t)Ly::R * Ly::KS + 2 + 2 * (size_t)Ly::R + (size_t)(NWARP + 1) * Ly::WS + (size_t)NWARP * DP +
+               (size_t)SEQ_BATCH * DP + 2 * SEQ_BATCH + SEQ_BATCH /*ib*/ + SEQ_BATCH / 2 /*uidb*/ + 4 * DP + 4 * NT_W +
+               Ly::PP + DP * DP + DP;
     size_t b = d * sizeof(double);
     b += 3 * (size_t)K_max * sizeof(int);
     b += ((size_t)Ly::PP * sizeof(unsigned short) + 15) & ~(size_t)15;
@@ -140,13 +158,13 @@ template <int DP> __host__ __device__ inline size_t fast_smem_bytes(int KS, int 
 template <int DP> __device__ inline FSmem<DP> fast_carve(double *base, const Params &p) {
     using Ly = Lay<DP>;
     FSmem<DP> s;
-    s.WS = fast_ws(p.KS);
     double *q = base;
-    s.rec = q; q += (size_t)Ly::R * p.KS;
+    s.rec = q; q += (size_t)Ly::R * Ly::KS;
     q = (double *)(((uintptr_t)q + 15) & ~(uintptr_t)15);
     s.prior = q; q += Ly::R;
     s.tmprec = q; q += Ly::R;
-    s.wrow = q; q += (size_t)NWARP * s.WS;
+    s.ew = q; q += (size_t)(NWARP + 1) * Ly::WS;
+    s.xw = q; q += (size_t)NWARP * DP;
     s.xb = q; q += SEQ_BATCH * DP;
     s.ub = q; q += SEQ_BATCH;
     s.lpb = q; q += SEQ_BATCH;
@@ -154,6 +172,7 @@ template <int DP> __device__ inline FSmem<DP> fast_carve(double *base, const Par
     s.uidb = (int *)q; q += SEQ_BATCH / 2;
     s.dv = q; q += 2 * DP;
     s.vv = q; q += 2 * DP;
+    s.nt = q; q += 4 * NT_W;
     s.A = q; q += Ly::PP;
     s.W = q; q += DP * DP;
     s.mm = q; q += DP;
@@ -168,122 +187,102 @@ template <int DP> __device__ inline FSmem<DP> fast_carve(double *base, const Par
 }
 
 // ---------------------------------------------------------------------------------------------
-// scalar pieces of a record
+// count table: row n of Params::ntab (see the NT_* enum).  One thread per count; `with_fixed` also writes the
+// entries that do not depend on the power.
 // ---------------------------------------------------------------------------------------------
-// Student-t constant for integer nu (gaussian_components.py:237-249): lgamma((nu+D)/2) - lgamma(nu/2)
-// - D/2 log(nu) - D/2 log(pi), tables indexed like the reference's (index = the integer itself).
-__device__ __forceinline__ double f_tc(const Params &p, long long nu) {
+static __global__ void k_fast_ntab(const Params p, long long rows, int with_fixed) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= rows) return;
     const int D = p.D;
-    return __ldg(p.lgam + nu + D) - __ldg(p.lgam + nu) - D / 2. * __ldg(p.logv + nu) - D / 2. * p.log_pi;
-}
-__device__ __forceinline__ double f_lf(const Params &p, double n) {
-    const double kap = p.k0 + n;
-    const double nu = (double)(p.v0 - p.D + 1) + n;
-    return log((kap + 1.) / (kap * nu));
-}
-// piece `which` (0 TC, 1 LF, 2 LC) of count n; n < 1 gives 0 (never used)
-__device__ __forceinline__ double f_piece(const Params &p, int which, double n) {
-    if (which == 0) return f_tc(p, p.v0 - p.D + 1 + (long long)n);
-    if (which == 1) return f_lf(p, n);
-    return n >= 1.0 ? log_count(n, p.power) : 0.0;
+    const double nn = (double)n;
+    const double kap = p.k0 + nn;
+    const long long nu = p.v0 - D + 1 + n;
+    double *row = p.ntab + (size_t)n * NT_W;
+    // Student-t constant for integer nu (gaussian_components.py:237-249): lgamma((nu+D)/2) - lgamma(nu/2)
+    // - D/2 log(nu) - D/2 log(pi), tables indexed like the reference's (index = the integer itself)
+    const double tc = p.lgam[nu + D] - p.lgam[nu] - D / 2. * p.logv[nu] - D / 2. * p.log_pi;
+    const double lf = log((kap + 1.) / (kap * (double)nu));
+    const double lc = n >= 1 ? log_count(nn, p.power) : 0.0;
+    row[NT_CN] = lc + tc - 0.5 * (D * lf);
+    if (with_fixed) {
+        row[NT_G] = kap / (kap + 1.);
+        row[NT_H] = ((double)nu + D) / 2.;
+        row[NT_BETA] = kap / (kap - 1.);
+        row[NT_RK] = 1. / kap;
+        row[5] = row[6] = row[7] = 0.0;
+    }
 }
 
-// derived scalars from (n, lds, current pieces, minus-one pieces); writes the NSC scalars with stride `st`
-__device__ __forceinline__ void f_write_scalars(const Params &p, double *sc, int st, double n, double lds, double tc,
-                                                double lf, double lc, double tcm, double lfm, double lcm, double cnt) {
-    const int D = p.D;
-    const double kap = p.k0 + n;
-    const double nu = (double)(p.v0 - D + 1) + n;
-    sc[F_N * st] = n;
-    sc[F_LDS * st] = lds;
-    sc[F_TC * st] = tc; sc[F_LF * st] = lf; sc[F_LC * st] = lc;
-    sc[F_TCM * st] = tcm; sc[F_LFM * st] = lfm; sc[F_LCM * st] = lcm;
-    sc[F_CW * st] = lc + tc - 0.5 * (D * lf + lds);
-    sc[F_G * st] = kap / (kap + 1.);
-    sc[F_H * st] = (nu + D) / 2.;
-    sc[F_BETA * st] = kap / (kap - 1.);
-    sc[F_CWO * st] = lcm + tcm - 0.5 * (D * lfm + lds);
-    sc[F_HO * st] = (nu - 1. + D) / 2. - 0.5;
-    sc[F_CNT * st] = cnt;
-    sc[F_SPARE * st] = 0.0;
+// scalars of a record with count n and log|S_N| = lds from the count-table rows of n - 1 (r0) and n (r1)
+__device__ __forceinline__ void f_write_scalars(double *sc, int st, double n, double lds, double cnt, const double *r0,
+                                                const double *r1) {
+    sc[(size_t)F_N * st] = n;
+    sc[(size_t)F_LDS * st] = lds;
+    sc[(size_t)F_CNT * st] = cnt;
+    sc[(size_t)F_CW * st] = r1[NT_CN] - 0.5 * lds;
+    sc[(size_t)F_G * st] = r1[NT_G];
+    sc[(size_t)F_H * st] = r1[NT_H];
+    sc[(size_t)F_BETA * st] = r1[NT_BETA];
+    sc[(size_t)F_CWO * st] = r0[NT_CN] - 0.5 * lds;
 }
 
 // ---------------------------------------------------------------------------------------------
-// evaluation: delta^T B delta with delta = m - x; col points at element 0 of the component, stride st
+// evaluation of one (datum, component) pair by one thread: exp(weight - wref), or weight - wref when want_log.
+//   other component: weight = log count prior + log_post_pred (crpmm.py:70-72)
+//   own component  : the same with the datum removed (del_item then log_post_pred, gaussian_components.py:171-186,
+//                    :228-251) in closed form: S_N' = S_N - beta d d^T, so |S_N'| = |S_N| om with
+//                    om = 1 - beta d^T B d, and 1 + q'/nu' = 1 / om.  NaN when om is too small to trust.
+// col points at element 0 of the component (compile-time stride ST); x in shared memory.
 // ---------------------------------------------------------------------------------------------
-template <int DP>
-__device__ __forceinline__ double f_quad(const double *__restrict__ col, int st, const double (&x)[DP]) {
+template <int DP, int ST>
+__device__ __noinline__ double f_eval_lane(const double *__restrict__ col, const double *__restrict__ x, int own,
+                                           double wref, int want_log) {
     using Ly = Lay<DP>;
     double d[DP];
-    const double *pm = col + (size_t)Ly::MU * st;
 #pragma unroll
-    for (int a = 0; a < DP; ++a) d[a] = pm[(size_t)a * st] - x[a];
-    const double *pb = col;
+    for (int a = 0; a < DP; ++a) d[a] = col[(Ly::MU + a) * ST] - x[a];
     double q = 0.0;
 #pragma unroll
     for (int a = 0; a < DP; ++a) {
         double r = 0.0;
 #pragma unroll
-        for (int b = 0; b < a; ++b) { r = fma(*pb, d[b], r); pb += st; }
-        r = fma(0.5 * (*pb), d[a], r);
-        pb += st;
+        for (int b = 0; b < a; ++b) r = fma(col[(a * (a + 1) / 2 + b) * ST], d[b], r);
+        r = fma(0.5 * col[(a * (a + 1) / 2 + a) * ST], d[a], r);
         q = fma(d[a], r, q);
     }
-    return 2.0 * q;
-}
-
-// weight of a component the datum is not in: log count prior + log_post_pred (crpmm.py:70-72)
-template <int DP>
-__device__ __forceinline__ double f_weight_other(const double *__restrict__ col, int st, const double (&x)[DP]) {
-    using Ly = Lay<DP>;
-    const double *sc = col + (size_t)Ly::SC * st;
-    const double q = f_quad<DP>(col, st, x);
-    return sc[F_CW * st] - sc[F_H * st] * log(1.0 + sc[F_G * st] * q);
-}
-// weight of the datum's own component with the datum removed (del_item then log_post_pred,
-// gaussian_components.py:171-186, :228-251) in closed form: S_N' = S_N - beta d d^T, so
-// |S_N'| = |S_N| om, om = 1 - beta d^T B d, and 1 + q'/nu' = 1 / om.
-template <int DP>
-__device__ __forceinline__ double f_weight_own(const double *__restrict__ col, int st, const double (&x)[DP], bool *ok) {
-    using Ly = Lay<DP>;
-    const double *sc = col + (size_t)Ly::SC * st;
-    const double q = f_quad<DP>(col, st, x);
-    const double om = 1.0 - sc[F_BETA * st] * q;
-    if (!(om > OM_MIN)) { *ok = false; return 0.0; }
-    return sc[F_CWO * st] + sc[F_HO * st] * log(om);
+    q *= 2.0;
+    const double *sc = col + Ly::SC * ST;
+    double arg, hh, cc;
+    if (own) {
+        arg = 1.0 - sc[F_BETA * ST] * q;
+        if (!(arg > OM_MIN)) return NAN;
+        hh = 1.0 - sc[F_H * ST];
+        cc = sc[F_CWO * ST];
+    } else {
+        arg = 1.0 + sc[F_G * ST] * q;
+        hh = sc[F_H * ST];
+        cc = sc[F_CW * ST];
+    }
+    const double t = (cc - hh * log(arg)) - wref;
+    if (want_log) return t;
+    return (t < EXP_CUTOFF) ? 0.0 : exp(t);
 }
 
 // ---------------------------------------------------------------------------------------------
-// logsumexp + draw (crpmm.py:75-78, utils.py:7-20) by one warp over n = K + 1 weights in shared memory.
-// Lane l owns the nb consecutive weights starting at l * nb.  Returns (all lanes) the drawn index; *margin is the
-// distance of u to the nearest boundary of the drawn interval (probability units); *bad is set when the
-// normaliser is not finite / positive.
+// draw (utils.py:7-20) by one warp from the n = K + 1 unnormalised probabilities e[] in shared memory: the first
+// index whose inclusive cumulative sum exceeds u * total, else the last index.  Lane l owns the nb consecutive
+// entries starting at l * nb.  Returns the index, or -2 when the total is not finite / positive (the caller falls
+// back to the log-domain draw).  *margin: distance of u to the nearest boundary of the drawn interval
+// (probability units, float accuracy -- a diagnostic).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int f_warp_draw(const double *__restrict__ w, int n, double u, double *margin, bool *bad) {
+static __device__ __noinline__ int f_warp_pick(const double *__restrict__ e, int n, double u, double *margin) {
     const int lane = threadIdx.x & 31;
     const int nb = (n + 31) >> 5;
     const int lo = lane * nb;
-    double v[NB_MAX];
-    float fm = -INFINITY;
-#pragma unroll
-    for (int t = 0; t < NB_MAX; ++t) {
-        v[t] = (t < nb && lo + t < n) ? w[lo + t] : -INFINITY;
-        fm = fmaxf(fm, __double2float_rn(v[t]));
-    }
-    int key = __float_as_int(fm);
-    key ^= (key >> 31) & 0x7fffffff;
-    key = __reduce_max_sync(0xffffffffu, key);
-    key ^= (key >> 31) & 0x7fffffff;
-    const double M = (double)__int_as_float(key);  // within float rounding of the true maximum: a safe scale
-    double c[NB_MAX];
+    const int hi = min(n, lo + nb);
     double run = 0.0;
-#pragma unroll
-    for (int t = 0; t < NB_MAX; ++t) {
-        const double dlt = v[t] - M;
-        const double e = (dlt < EXP_CUTOFF) ? 0.0 : exp(dlt);
-        run += (t < nb) ? e : 0.0;
-        c[t] = run;
-    }
+#pragma unroll 1
+    for (int t = lo; t < hi; ++t) run += e[t];
     double incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -295,14 +294,13 @@ __device__ __forceinline__ int f_warp_draw(const double *__restrict__ w, int n, 
     const double s = __shfl_sync(0xffffffffu, incl, 31);
     const double t0 = u * s;
     int cand = -1;
-    double lower = excl, mg = 0.0;
-#pragma unroll
-    for (int t = 0; t < NB_MAX; ++t) {
-        if (cand < 0 && t < nb && lo + t < n) {
-            const double upper = excl + c[t];
-            if (upper > t0) { cand = lo + t; mg = fmin(t0 - lower, upper - t0); }
-            lower = upper;
-        }
+    double lower = excl, mg = 0.0, cum = 0.0;
+#pragma unroll 1
+    for (int t = lo; t < hi; ++t) {
+        cum += e[t];
+        const double upper = excl + cum;
+        if (upper > t0) { cand = t; mg = fmin(t0 - lower, upper - t0); break; }
+        lower = upper;
     }
     const unsigned who = __ballot_sync(0xffffffffu, cand >= 0);
     int k;
@@ -312,11 +310,31 @@ __device__ __forceinline__ int f_warp_draw(const double *__restrict__ w, int n, 
     } else {
         const int src = __ffs(who) - 1;
         k = __shfl_sync(0xffffffffu, cand, src);
-        mg = __shfl_sync(0xffffffffu, mg, src) / s;
+        mg = __shfl_sync(0xffffffffu, mg, src);
+        mg = (double)__fdividef((float)mg, (float)s);
     }
     *margin = mg;
-    *bad = !(s > 0.0) || !(s < INFINITY);
+    if (!(s > 0.0) || !(s < INFINITY)) k = -2;
     return k;
+}
+
+// log-domain version (crpmm.py:75: exp(w - logsumexp(w))) for weights whose spread overflows the fast scaling:
+// w[] holds weight - wref; scaled by (a float rounding of) the maximum.  In place: w[] becomes the exponentials.
+static __device__ __noinline__ int f_warp_draw_log(double *__restrict__ w, int n, double u, double *margin) {
+    const int lane = threadIdx.x & 31;
+    float fm = -INFINITY;
+    for (int t = lane; t < n; t += 32) fm = fmaxf(fm, __double2float_rn(w[t]));
+    int key = __float_as_int(fm);
+    key ^= (key >> 31) & 0x7fffffff;
+    key = __reduce_max_sync(0xffffffffu, key);
+    key ^= (key >> 31) & 0x7fffffff;
+    const double M = (double)__int_as_float(key);
+    for (int t = lane; t < n; t += 32) {
+        const double dlt = w[t] - M;
+        w[t] = (dlt < EXP_CUTOFF) ? 0.0 : exp(dlt);
+    }
+    __syncwarp();
+    return f_warp_pick(w, n, u, margin);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -326,9 +344,9 @@ __device__ __forceinline__ int f_warp_draw(const double *__restrict__ w, int n, 
 // alone (n = 0, :161-164).  out has stride ost.  Returns false (all lanes) if S_N is not positive definite.
 // ---------------------------------------------------------------------------------------------
 template <int DP>
-__device__ bool f_exact_record_warp(const Params &p, int mode, const double *num_g, const double *S_g, double n_after,
-                                    const double *xrm, const unsigned short *rc, double *A, double *W, double *mm,
-                                    double *out, int ost) {
+__device__ __noinline__ bool f_exact_record_warp(const Params &p, int mode, const double *num_g, const double *S_g,
+                                                 double n_after, const double *xrm, const unsigned short *rc, double *A,
+                                                 double *W, double *mm, double *out, int ost) {
     using Ly = Lay<DP>;
     const int lane = threadIdx.x & 31;
     const int D = p.D;
@@ -390,72 +408,79 @@ __device__ bool f_exact_record_warp(const Params &p, int mode, const double *num
         out[(size_t)e * ost] = sacc;
     }
     for (int r = lane; r < DP; r += 32) out[(size_t)(Ly::MU + r) * ost] = (r < D) ? mm[r] : 0.0;
-    // scalar pieces: lanes 0..5
-    double piece = 0.0;
-    if (lane < 3) piece = f_piece(p, lane, n_after);
-    else if (lane < 6) piece = (n_after >= 2.0) ? f_piece(p, lane - 3, n_after - 1.0) : 0.0;
-    const double tc = __shfl_sync(0xffffffffu, piece, 0), lf = __shfl_sync(0xffffffffu, piece, 1);
-    const double lc = __shfl_sync(0xffffffffu, piece, 2), tcm = __shfl_sync(0xffffffffu, piece, 3);
-    const double lfm = __shfl_sync(0xffffffffu, piece, 4), lcm = __shfl_sync(0xffffffffu, piece, 5);
-    if (lane == 0) f_write_scalars(p, out + (size_t)Ly::SC * ost, ost, n_after, lds, tc, lf, lc, tcm, lfm, lcm, 0.0);
+    if (lane == 0) {
+        const long long n1 = (long long)n_after;
+        const double *r1 = p.ntab + (size_t)n1 * NT_W;
+        const double *r0 = p.ntab + (size_t)(n1 > 0 ? n1 - 1 : 0) * NT_W;
+        f_write_scalars(out + (size_t)Ly::SC * ost, ost, n_after, lds, 0.0, r0, r1);
+    }
     __syncwarp();
     return true;
 }
 
 // ---------------------------------------------------------------------------------------------
-// rank-one update of one record by ONE WARP.  sign = -1: the datum leaves (del_item), sign = +1: it joins
-// (add_item).  x in shared memory.  Writes B, m; leaves log|S_N|' and n' in sh.lds_new / sh.n_new [which].
+// rank-one update of one record by ONE WARP, including its scalars.  sign = -1: the datum leaves (del_item),
+// sign = +1: it joins (add_item).  x in shared memory.  which = 0 (removal) / 1 (addition) selects the scratch.
 // ---------------------------------------------------------------------------------------------
 template <int DP>
-__device__ void f_rank_one_warp(const Params &p, const FSmem<DP> &s, int k, int sign, const double *x, int which) {
+__device__ __noinline__ void f_rank_one_warp(const Params &p, const FSmem<DP> &s, int k, int sign, const double *x,
+                                             int which, int seq) {
     using Ly = Lay<DP>;
+    constexpr int ST = Ly::KS;
     const int lane = threadIdx.x & 31;
-    const int st = p.KS;
     double *col = s.rec + k;
-    double *dv = s.dv + which * DP, *vv = s.vv + which * DP;
-    const double n = col[(size_t)(Ly::SC + F_N) * st];
-    const double kap = p.k0 + n;
-    if (lane < DP) dv[lane] = x[lane] - col[(size_t)(Ly::MU + lane) * st];
+    double *dv = s.dv + which * DP, *vv = s.vv + which * DP, *nt = s.nt + which * 2 * NT_W;
+    double *sc = col + Ly::SC * ST;
+    const double n = sc[F_N * ST];
+    const double n2 = n + (double)sign;
+    // count-table rows n2 - 1 and n2 (adjacent: 2 * NT_W doubles), in flight while the matrix work runs
+    double ntv = 0.0;
+    if (lane < 2 * NT_W) ntv = __ldg(p.ntab + (size_t)((long long)n2 - 1) * NT_W + lane);
+    // d = x - m, v = B d: lane (part, r) sums its share of row r, parts combined by shuffles
+    const int r = lane % DP, part = lane / DP;
+    constexpr int NH = 32 / DP;
+    constexpr int BS = (DP + NH - 1) / NH;
+    const double dr = x[r] - col[(Ly::MU + r) * ST];
+    if (part == 0) dv[r] = dr;
     __syncwarp();
-    if (lane < DP) {
-        double acc = 0.0;
+    double acc = 0.0;
 #pragma unroll
-        for (int b = 0; b < DP; ++b) {
-            const int e = (lane >= b) ? row_idx(lane, b) : row_idx(b, lane);
-            acc = fma(col[(size_t)e * st], dv[b], acc);
+    for (int t = 0; t < BS; ++t) {
+        const int b = part * BS + t;
+        if (b < DP) {
+            const int e = (r >= b) ? row_idx(r, b) : row_idx(b, r);
+            acc = fma(col[e * ST], dv[b], acc);
         }
-        vv[lane] = acc;
     }
-    __syncwarp();
-    double sq = 0.0;
 #pragma unroll
-    for (int b = 0; b < DP; ++b) sq = fma(dv[b], vv[b], sq);
-    double gam, kap2, lds_add;
-    if (sign < 0) {
-        const double beta = kap / (kap - 1.);
-        const double om = 1.0 - beta * sq;
-        gam = beta / om;
-        kap2 = kap - 1.;
-        lds_add = log(om);
-    } else {
-        const double beta = kap / (kap + 1.);
-        const double den = 1.0 + beta * sq;
-        gam = -beta / den;
-        kap2 = kap + 1.;
-        lds_add = log(den);
-    }
+    for (int o = DP; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (part == 0) vv[r] = acc;
+    double sq = dr * acc;
+#pragma unroll
+    for (int o = DP / 2; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane < 2 * NT_W) nt[lane] = ntv;
+    __syncwarp();
+    // beta = kappa / (kappa -+ 1): BETA(n) for a removal, G(n) for an addition
+    const double beta = (sign < 0) ? sc[F_BETA * ST] : sc[F_G * ST];
+    const double den = (sign < 0) ? 1.0 - beta * sq : 1.0 + beta * sq;
+    const double gam = (sign < 0) ? beta / den : -beta / den;
+    const double rk2 = nt[NT_W + NT_RK];   // 1 / kappa(n2)
+#pragma unroll 1
     for (int e = lane; e < Ly::PP; e += 32) {
         const int a = s.rc[e] >> 8, b = s.rc[e] & 0xff;
-        double *pe = col + (size_t)e * st;
+        double *pe = col + e * ST;
         *pe = fma(gam * vv[a], vv[b], *pe);
     }
-    if (lane < DP) {
-        double *pm = col + (size_t)(Ly::MU + lane) * st;
-        *pm = (sign < 0) ? (*pm - dv[lane] / kap2) : (*pm + dv[lane] / kap2);
+    if (part == 0) {
+        double *pm = col + (Ly::MU + r) * ST;
+        *pm = fma((sign < 0) ? -dr : dr, rk2, *pm);
     }
     if (lane == 0) {
-        s.sh->lds_new[which] = col[(size_t)(Ly::SC + F_LDS) * st] + lds_add;
-        s.sh->n_new[which] = n + (double)sign;
+        const double cnt = sc[F_CNT * ST] + 1.0;
+        f_write_scalars(sc, ST, n2, sc[F_LDS * ST] + log(den), cnt, nt, nt + NT_W);
+        FSh &sh = *s.sh;
+        if (cnt >= (double)REFRESH_EVERY) { if (which == 0) sh.refresh_a = seq; else sh.refresh_b = seq; }
+        if (which == 1) sh.moves += 1;
     }
     __syncwarp();
 }
@@ -463,12 +488,13 @@ __device__ void f_rank_one_warp(const Params &p, const FSmem<DP> &s, int k, int 
 // bit-exact statistics update in global memory by `nthr` threads of CTA 0 (thread rank t):
 // S -= / += fl(x_a x_b), num -= / += x_a   (gaussian_components.py:165-166, :184-185)
 template <int DP>
-__device__ __forceinline__ void f_stats_axpy(const Params &p, const unsigned short *rc, int slot, const double *x,
-                                             int sign, bool init_prior, int t, int nthr) {
+__device__ __noinline__ void f_stats_axpy(const Params &p, const unsigned short *rc, int slot, const double *x, int sign,
+                                          int init_prior, int t, int nthr) {
     using Ly = Lay<DP>;
     const int D = p.D;
     double *S = p.S + (size_t)slot * Ly::PP;
     double *num = p.num + (size_t)slot * DP;
+#pragma unroll 1
     for (int e = t; e < Ly::NS; e += nthr) {
         if (e < Ly::PP) {
             const int a = rc[e] >> 8, b = rc[e] & 0xff;
@@ -486,210 +512,256 @@ __device__ __forceinline__ void f_stats_axpy(const Params &p, const unsigned sho
 }
 
 // ---------------------------------------------------------------------------------------------
-// Resolve ONE datum (whole CTA, every CTA identically).  Inputs in the staging buffers at index jj.
+// rare paths of a step, out of line
 // ---------------------------------------------------------------------------------------------
+// del_item empties the component: del_component (gaussian_components.py:188-205), swap with the last slot
+template <int DP> __device__ __noinline__ void f_delete_component(const Params &p, const FSmem<DP> &s, int k_old) {
+    using Ly = Lay<DP>;
+    constexpr int ST = Ly::KS;
+    FSh &sh = *s.sh;
+    const int tid = threadIdx.x;
+    const int L = sh.K - 1;
+    __syncthreads();
+    if (k_old != L) {
+        for (int e = tid; e < Ly::R; e += TF) s.rec[(size_t)e * ST + k_old] = s.rec[(size_t)e * ST + L];
+        if (blockIdx.x == 0) {
+            for (int e = tid; e < Ly::PP; e += TF)
+                __stcg(p.S + (size_t)k_old * Ly::PP + e, __ldcg(p.S + (size_t)L * Ly::PP + e));
+            for (int e = tid; e < DP; e += TF) __stcg(p.num + (size_t)k_old * DP + e, __ldcg(p.num + (size_t)L * DP + e));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int uid_dead = s.uid_of_slot[k_old];
+        if (k_old != L) {
+            const int uid_l = s.uid_of_slot[L];
+            s.uid_of_slot[k_old] = uid_l;
+            s.slot_of_uid[uid_l] = k_old;
+        }
+        s.uid_of_slot[L] = -1;
+        s.slot_of_uid[uid_dead] = -1;
+        s.uid_free[sh.n_free] = uid_dead;
+        sh.n_free += 1;
+        sh.K = L;
+        sh.deaths += 1;
+    }
+    __syncthreads();
+}
+
+// the closed form of the own-component weight is not trusted: build the reduced component's record exactly from
+// the statistics (every CTA; CTA 0's statistics writes are made visible by the first barrier, and stay frozen until
+// every replica has read them by the second).  Leaves the entry of k_old in ew[].
 template <int DP>
-__device__ void f_step(const Params &p, const FSmem<DP> &s, int jj) {
+__device__ __noinline__ void f_explicit_own(const Params &p, const FSmem<DP> &s, int k_old, double n_old,
+                                            const double *xs, double wref, double *ew, int seq) {
     using Ly = Lay<DP>;
     FSh &sh = *s.sh;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int st = p.KS;
-    const bool cta0 = (blockIdx.x == 0);
-    const double *xs = s.xb + jj * DP;
-
-    if (tid == 0) {
-        const int uid = s.uidb[jj];
-        int k_old = -1;
-        double n_old = 0.0;
-        if (uid >= 0) { k_old = s.slot_of_uid[uid]; n_old = s.rec[(size_t)(Ly::SC + F_N) * st + k_old]; }
-        sh.i = s.ib[jj]; sh.uid = uid; sh.k_old = k_old; sh.n_old = n_old;
-        sh.u = s.ub[jj]; sh.lp = s.lpb[jj];
-        sh.died = 0; sh.need_explicit = 0; sh.explicit_done = 0; sh.refresh_a = 0; sh.refresh_b = 0;
-    }
-    __syncthreads();
-    const int k_old = sh.k_old;
-    const long long i = sh.i;
-    bool died = false;
-    if (k_old >= 0 && sh.n_old == 1.0) {
-        // del_item empties the component: del_component (gaussian_components.py:188-205), swap with the last slot
-        const int L = sh.K - 1;
-        if (k_old != L) {
-            for (int e = tid; e < Ly::R; e += TF) s.rec[(size_t)e * st + k_old] = s.rec[(size_t)e * st + L];
-            if (cta0) {
-                for (int e = tid; e < Ly::PP; e += TF)
-                    __stcg(p.S + (size_t)k_old * Ly::PP + e, __ldcg(p.S + (size_t)L * Ly::PP + e));
-                for (int e = tid; e < DP; e += TF)
-                    __stcg(p.num + (size_t)k_old * DP + e, __ldcg(p.num + (size_t)L * DP + e));
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const int uid_dead = s.uid_of_slot[k_old];
-            if (k_old != L) {
-                const int uid_l = s.uid_of_slot[L];
-                s.uid_of_slot[k_old] = uid_l;
-                s.slot_of_uid[uid_l] = k_old;
-            }
-            s.uid_of_slot[L] = -1;
-            s.slot_of_uid[uid_dead] = -1;
-            s.uid_free[sh.n_free] = uid_dead;
-            sh.n_free += 1;
-            sh.K = L;
-            sh.deaths += 1;
-            sh.died = 1;
-        }
-        died = true;
-        __syncthreads();
-    }
-    const int K = sh.K;
-
-    // weights of the live components (crpmm.py:68-74): thread k evaluates component k
-    if (tid < K) {
-        double x[DP];
-#pragma unroll
-        for (int a = 0; a < DP; ++a) x[a] = xs[a];
-        double w;
-        if (tid == k_old && !died) {
-            bool ok = true;
-            w = f_weight_own<DP>(s.rec + tid, st, x, &ok);
-            if (!ok) sh.need_explicit = 1;
-        } else {
-            w = f_weight_other<DP>(s.rec + tid, st, x);
-        }
-        s.wrow[tid] = w;
-    }
-    if (tid == K) s.wrow[K] = p.log_alpha + sh.lp;
-    __syncthreads();
-
-    if (sh.need_explicit) {
-        // the closed form is not trusted: build the reduced component's record exactly from the statistics
-        // (every CTA; CTA 0's statistics writes are made visible by the barrier)
-        f_grid_barrier(p.ctl);
-        if (warp == 0) {
-            const bool okf = f_exact_record_warp<DP>(p, 0, p.num + (size_t)k_old * DP, p.S + (size_t)k_old * Ly::PP,
-                                                     sh.n_old - 1.0, xs, s.rc, s.A, s.W, s.mm, s.tmprec, 1);
-            if (!okf) { if (lane == 0) sh.error = -4; }
-            else if (lane == 0) {
-                double x[DP];
-#pragma unroll
-                for (int a = 0; a < DP; ++a) x[a] = xs[a];
-                s.wrow[k_old] = f_weight_other<DP>(s.tmprec, 1, x);
-                sh.explicit_done = 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    f_grid_barrier(p.ctl);
+    if (warp == 0) {
+        const bool okf = f_exact_record_warp<DP>(p, 0, p.num + (size_t)k_old * DP, p.S + (size_t)k_old * Ly::PP,
+                                                 n_old - 1.0, xs, s.rc, s.A, s.W, s.mm, s.tmprec, 1);
+        if (lane == 0) {
+            if (!okf) {
+                sh.error = -4;
+            } else {
+                ew[k_old] = f_eval_lane<DP, 1>(s.tmprec, xs, 0, wref, 0);
+                sh.explicit_done = seq;
                 sh.explicit_evals += 1;
             }
         }
-        // CTA 0 must not touch the statistics again before every replica has read them
-        f_grid_barrier(p.ctl);
     }
+    f_grid_barrier(p.ctl);
+}
 
+// the weights' spread overflowed the exp scale of the fast draw: redo the datum in the log domain
+template <int DP>
+__device__ __noinline__ void f_log_domain_draw(const Params &p, const FSmem<DP> &s, int K, int k_old, bool own_live,
+                                               bool expl, const double *xs, double wref, double u, double *ew) {
+    using Ly = Lay<DP>;
+    FSh &sh = *s.sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < K) {
+        if (expl && tid == k_old) ew[tid] = f_eval_lane<DP, 1>(s.tmprec, xs, 0, wref, 1);
+        else ew[tid] = f_eval_lane<DP, Ly::KS>(s.rec + tid, xs, (own_live && tid == k_old) ? 1 : 0, wref, 1);
+    } else if (tid == K) {
+        ew[K] = 0.0;
+    }
+    __syncthreads();
     if (warp == 0) {
         double mg;
-        bool bad;
-        const int k = f_warp_draw(s.wrow, K + 1, sh.u, &mg, &bad);
+        const int k = f_warp_draw_log(ew, K + 1, u, &mg);
         if (lane == 0) {
             sh.k_new = k;
-            sh.margin = mg;
-            if (bad) sh.error = -4;
+            if (k < 0) sh.error = -4;
             sh.evals += K;
             const unsigned long long mb = (unsigned long long)__double_as_longlong(mg);
             if (mb < sh.margin_bits) sh.margin_bits = mb;
         }
     }
     __syncthreads();
+}
+
+// drift control: rebuild record(s) from the bit-exact statistics (every CTA; two barriers as above)
+template <int DP>
+__device__ __noinline__ void f_refresh(const Params &p, const FSmem<DP> &s, int ka, double n_a, int kb, double n_b) {
+    using Ly = Lay<DP>;
+    FSh &sh = *s.sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    f_grid_barrier(p.ctl);
+    if (warp == 0) {
+        bool okf = true;
+        int cnt = 0;
+        if (ka >= 0) {
+            okf = f_exact_record_warp<DP>(p, 0, p.num + (size_t)ka * DP, p.S + (size_t)ka * Ly::PP, n_a, nullptr, s.rc, s.A,
+                                          s.W, s.mm, s.rec + ka, Ly::KS);
+            ++cnt;
+        }
+        if (okf && kb >= 0) {
+            okf = f_exact_record_warp<DP>(p, 0, p.num + (size_t)kb * DP, p.S + (size_t)kb * Ly::PP, n_b, nullptr, s.rc, s.A,
+                                          s.W, s.mm, s.rec + kb, Ly::KS);
+            ++cnt;
+        }
+        if (lane == 0) {
+            if (!okf) sh.error = -4;
+            sh.refreshes += cnt;
+        }
+    }
+    f_grid_barrier(p.ctl);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resolve ONE datum (whole CTA, every CTA identically).  Inputs in the staging buffers at index jj; seq is a
+// per-step sequence number (> 0) used to tag the rare-path flags so they never need resetting.
+// ---------------------------------------------------------------------------------------------
+template <int DP>
+__device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj, int seq) {
+    using Ly = Lay<DP>;
+    constexpr int ST = Ly::KS;
+    FSh &sh = *s.sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool cta0 = (blockIdx.x == 0);
+    const double *xs = s.xb + jj * DP;
+    double *ew = s.ew + (size_t)NWARP * Ly::WS;
+
+    // head: every thread derives the same values from the replicated state
+    const int uid = s.uidb[jj];
+    int k_old = -1;
+    double n_old = 0.0;
+    if (uid >= 0) { k_old = s.slot_of_uid[uid]; n_old = s.rec[(Ly::SC + F_N) * ST + k_old]; }
+    bool died = false;
+    if (k_old >= 0 && n_old == 1.0) {
+        f_delete_component<DP>(p, s, k_old);
+        died = true;
+    }
+    const int K = sh.K;
+    const double wref = p.log_alpha + s.lpb[jj];   // the new-table weight (crpmm.py:74) is the exp scale
+    const bool own_live = (k_old >= 0) && !died;
+
+    // phase A: exp(weight - wref) of every live component (crpmm.py:68-75), thread k evaluates component k
+    if (tid < K) {
+        const double e = f_eval_lane<DP, ST>(s.rec + tid, xs, (own_live && tid == k_old) ? 1 : 0, wref, 0);
+        if (e != e) sh.need_explicit = seq;
+        ew[tid] = e;
+    } else if (tid == K) {
+        ew[K] = 1.0;
+    }
+    __syncthreads();
+    F_PROF(PH_EVAL);
+    bool expl = false;
+    if (sh.need_explicit == seq) {
+        f_explicit_own<DP>(p, s, k_old, n_old, xs, wref, ew, seq);
+        expl = (sh.explicit_done == seq);
+        F_PROF(PH_RARE);
+    }
+
+    // phase B: the draw (crpmm.py:75-78, utils.py:7-20)
+    if (warp == 0) {
+        double mg;
+        const int k = f_warp_pick(ew, K + 1, s.ub[jj], &mg);
+        if (lane == 0) {
+            sh.k_new = k;
+            if (k >= 0) {
+                sh.evals += K;
+                const unsigned long long mb = (unsigned long long)__double_as_longlong(mg);
+                if (mb < sh.margin_bits) sh.margin_bits = mb;
+            }
+        }
+    }
+    __syncthreads();
+    if (sh.k_new == -2) f_log_domain_draw<DP>(p, s, K, k_old, own_live, expl, xs, wref, s.ub[jj], ew);
+    F_PROF(PH_DRAW);
+    if (tid == 0 && cta0) sh.prof[PH_STEPS] += 1;
     if (sh.error) return;
     const int k_new = sh.k_new;
     if (k_new == k_old && !died) return;  // stay: nothing was touched (crpmm.py:82-85)
 
-    // ---- the datum moves: add_item (gaussian_components.py:154-169) ----
+    // phase C: the datum moves: add_item (gaussian_components.py:154-169)
     const bool birth = (k_new == K);
     if (birth) {
-        if (K >= p.K_max) { if (tid == 0) sh.error = -3; __syncthreads(); return; }
-        if (K >= p.Kcap) {  // nothing has been changed for this datum yet: the generic engine redoes it
+        if (K >= p.K_max) { __syncthreads(); if (tid == 0) sh.error = -3; __syncthreads(); return; }
+        if (K >= Ly::KCAP) {  // nothing has been changed for this datum yet: the generic engine redoes it
+            __syncthreads();
             if (tid == 0) { sh.error = E_NEED_GENERIC; sh.evals -= K; }
             __syncthreads();
             return;
         }
-        for (int e = tid; e < Ly::R; e += TF) s.rec[(size_t)e * st + K] = s.prior[e];
+        for (int e = tid; e < Ly::R; e += TF) s.rec[(size_t)e * ST + K] = s.prior[e];
         if (tid == 0) {
-            const int uid = s.uid_free[sh.n_free - 1];
+            const int nuid = s.uid_free[sh.n_free - 1];
             sh.n_free -= 1;
-            s.uid_of_slot[K] = uid;
-            s.slot_of_uid[uid] = K;
+            s.uid_of_slot[K] = nuid;
+            s.slot_of_uid[nuid] = K;
             sh.K = K + 1;
             sh.births += 1;
         }
+        __syncthreads();
     }
-    const bool remove_now = (k_old >= 0) && !died;
-    const bool expl = sh.explicit_done != 0;
-    __syncthreads();
-    // update phase: warps 0/1 the two records, warps 2..7 the fresh scalar pieces, CTA 0 warps 8.. the statistics
-    const double n_a = remove_now ? sh.n_old - 1.0 : 0.0;
-    const double n_b = s.rec[(size_t)(Ly::SC + F_N) * st + k_new] + 1.0;
+    const bool remove_now = own_live;
     if (warp == 0) {
         if (remove_now) {
             if (expl) {
-                for (int e = lane; e < Ly::R; e += 32) s.rec[(size_t)e * st + k_old] = s.tmprec[e];
+                for (int e = lane; e < Ly::R; e += 32) s.rec[(size_t)e * ST + k_old] = s.tmprec[e];
             } else {
-                f_rank_one_warp<DP>(p, s, k_old, -1, xs, 0);
+                f_rank_one_warp<DP>(p, s, k_old, -1, xs, 0, seq);
             }
         }
     } else if (warp == 1) {
-        f_rank_one_warp<DP>(p, s, k_new, +1, xs, 1);
-    } else if (warp < 5) {
-        // component a after the removal: its minus-one pieces are new (count n_a - 1)
-        if (lane == 0 && remove_now && !expl) sh.fresh[0][warp - 2] = (n_a >= 2.0) ? f_piece(p, warp - 2, n_a - 1.0) : 0.0;
-    } else if (warp < 8) {
-        // component b after the addition: its current pieces are new (count n_b)
-        if (lane == 0) sh.fresh[1][warp - 5] = f_piece(p, warp - 5, n_b);
-    } else if (cta0) {
-        const int t = tid - 8 * 32, nthr = TF - 8 * 32;
-        if (remove_now) f_stats_axpy<DP>(p, s.rc, k_old, xs, -1, false, t, nthr);
-        f_stats_axpy<DP>(p, s.rc, k_new, xs, +1, birth, t, nthr);
-        if (t == 0) __stcg(p.z_out + i, s.uid_of_slot[k_new]);  // replicas keep reading the sweep's input labels
-    }
-    __syncthreads();
-    if (tid == 0 && remove_now && !expl) {
-        double *sc = s.rec + (size_t)Ly::SC * st + k_old;
-        const double cnt = sc[F_CNT * st] + 1.0;
-        // the old minus-one pieces become the current ones
-        f_write_scalars(p, sc, st, sh.n_new[0], sh.lds_new[0], sc[F_TCM * st], sc[F_LFM * st], sc[F_LCM * st],
-                        sh.fresh[0][0], sh.fresh[0][1], sh.fresh[0][2], cnt);
-        if (cnt >= (double)REFRESH_EVERY) sh.refresh_a = 1;
-    }
-    if (tid == 32) {
-        double *sc = s.rec + (size_t)Ly::SC * st + k_new;
-        const double cnt = sc[F_CNT * st] + 1.0;
-        // the old current pieces become the minus-one ones
-        const double tcm = birth ? 0.0 : sc[F_TC * st], lfm = birth ? 0.0 : sc[F_LF * st], lcm = birth ? 0.0 : sc[F_LC * st];
-        f_write_scalars(p, sc, st, sh.n_new[1], sh.lds_new[1], sh.fresh[1][0], sh.fresh[1][1], sh.fresh[1][2], tcm, lfm,
-                        lcm, cnt);
-        if (cnt >= (double)REFRESH_EVERY) sh.refresh_b = 1;
-        sh.moves += 1;
-    }
-    __syncthreads();
-    if (sh.refresh_a || sh.refresh_b) {
-        // drift control: rebuild the record(s) from the bit-exact statistics (every CTA; one barrier)
-        f_grid_barrier(p.ctl);
-        if (warp == 0) {
-            bool okf = true;
-            if (sh.refresh_a)
-                okf = f_exact_record_warp<DP>(p, 0, p.num + (size_t)k_old * DP, p.S + (size_t)k_old * Ly::PP, n_a, nullptr,
-                                              s.rc, s.A, s.W, s.mm, s.rec + k_old, st);
-            if (okf && sh.refresh_b)
-                okf = f_exact_record_warp<DP>(p, 0, p.num + (size_t)k_new * DP, p.S + (size_t)k_new * Ly::PP, n_b, nullptr,
-                                              s.rc, s.A, s.W, s.mm, s.rec + k_new, st);
-            if (lane == 0) {
-                if (!okf) sh.error = -4;
-                sh.refreshes += (sh.refresh_a ? 1 : 0) + (sh.refresh_b ? 1 : 0);
-            }
+        f_rank_one_warp<DP>(p, s, k_new, +1, xs, 1, seq);
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // what this step changed, for the evaluators' cached rows
+            sh.ver += 1;
+            sh.dirty_a = remove_now ? k_old : -1;
+            sh.dirty_b = k_new;
+            sh.dirty_all = (died || expl) ? 1 : 0;
         }
-        f_grid_barrier(p.ctl);  // as above: statistics stay frozen until every replica has read them
+    } else if (cta0 && warp >= 8) {
+        // CTA 0: the bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition)
+        if (warp < 12) {
+            if (remove_now) f_stats_axpy<DP>(p, s.rc, k_old, xs, -1, 0, tid - 256, 128);
+        } else {
+            f_stats_axpy<DP>(p, s.rc, k_new, xs, +1, birth ? 1 : 0, tid - 384, 128);
+            if (tid == 384) __stcg(p.z_out + s.ib[jj], s.uid_of_slot[k_new]);  // replicas keep reading the input labels
+        }
+    }
+    __syncthreads();
+    F_PROF(PH_UPDATE);
+    if (tid == 0 && cta0) sh.prof[PH_MOVES] += 1;
+    const bool ra = (sh.refresh_a == seq), rb = (sh.refresh_b == seq);
+    if (ra || rb) {
+        const double n_a = ra ? s.rec[(Ly::SC + F_N) * ST + k_old] : 0.0;
+        const double n_b = s.rec[(Ly::SC + F_N) * ST + k_new];
+        f_refresh<DP>(p, s, ra ? k_old : -1, n_a, rb ? k_new : -1, n_b);
+        if (tid == 0) sh.dirty_all = 1;
+        __syncthreads();
+        F_PROF(PH_RARE);
     }
 }
 
 // stage `nb` data starting at scan position pos into the buffers, then resolve them in order
 template <int DP>
-__device__ int f_run(const Params &p, const FSmem<DP> &s, long long pos, int nb) {
+__device__ int f_run(const Params &p, const FSmem<DP> &s, long long pos, int nb, int &seq) {
     const int tid = threadIdx.x;
     for (int t = tid; t < nb * DP; t += TF) {
         const int jj = t / DP, a = t % DP;
@@ -704,9 +776,11 @@ __device__ int f_run(const Params &p, const FSmem<DP> &s, long long pos, int nb)
         }
     }
     __syncthreads();
+    F_PROF(PH_STAGE);
     int done = 0;
     for (int jj = 0; jj < nb; ++jj) {
-        f_step<DP>(p, s, jj);
+        seq += 1;
+        f_step<DP>(p, s, jj, seq);
         if (s.sh->error) break;
         done = jj + 1;
     }
@@ -715,72 +789,109 @@ __device__ int f_run(const Params &p, const FSmem<DP> &s, long long pos, int nb)
 
 // ---------------------------------------------------------------------------------------------
 // speculative evaluation of the window [pos, pos + win): a warp per datum, lanes over components.
-// Scan position j is owned by CTA (j % grid), warp ((j / grid) % NWARP) -- a fixed owner, so the rows of X a
-// warp re-evaluates after a mover are already in its SM's L1.
+// Scan position j is owned by CTA (j % grid), warp ((j / grid) % NWARP) -- a fixed owner, so after a mover the
+// warp still holds the datum it is asked to evaluate again: its inputs (WCache + xw) and its row of
+// exponentials ew[], of which only the entries of the components the mover touched are recomputed.
+// A candidate (anything but a provable "stay") is published with its inputs: mover slot of this warp, then
+// atomicMin of (position << 12 | global warp id).
 // ---------------------------------------------------------------------------------------------
+struct WCache {
+    long long j, i;   // scan position / datum held (-1: none)
+    int uid;
+    int ver;          // record version the row ew[] was evaluated at (-1: no row)
+    int K;            // its length - 1
+    double u, lp;
+};
+
 template <int DP>
 __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos, long long win, int K,
-                              unsigned long long *first_slot) {
+                              unsigned long long *first_slot, WCache &c) {
     using Ly = Lay<DP>;
+    constexpr int ST = Ly::KS;
+    const FSh &sh = *s.sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int st = p.KS;
     const long long G = gridDim.x;
     const long long end = pos + win;
-    double *wrow = s.wrow + (size_t)warp * s.WS;
-    // first scan position >= pos owned by this warp
+    double *ew = s.ew + (size_t)warp * Ly::WS;
+    double *xw = s.xw + (size_t)warp * DP;
     const long long stride = G * NWARP;
     const long long own = (long long)blockIdx.x + G * warp;  // j % stride == own
+    const unsigned long long gw = (unsigned long long)(blockIdx.x * NWARP + warp);
     long long j = pos - (pos % stride) + own;
     if (j < pos) j += stride;
+    const int ver = sh.ver;
     double my_margin = 1.0;
     for (; j < end; j += stride) {
         long long known = 0;
-        if (lane == 0) known = (long long)__ldcg(first_slot);
+        if (lane == 0) known = (long long)(__ldcg(first_slot) >> 12);
         known = __shfl_sync(0xffffffffu, known, 0);
         if (known < j) break;  // an earlier candidate is already known: this datum would be redone
-        const long long i = p.order ? p.order[j] : j;
-        const int uid = __ldcg(p.z_uid + i);
+        if (c.j != j) {
+            const long long i = p.order ? p.order[j] : j;
+            c.j = j; c.i = i; c.ver = -1;
+            c.uid = __ldcg(p.z_uid + i);
+            c.u = p.u[j];
+            c.lp = p.log_prior[i];
+            __syncwarp();
+            if (lane < DP) xw[lane] = p.X[(size_t)i * DP + lane];
+            __syncwarp();
+        }
+        const int uid = c.uid;
         bool cand = (uid < 0);
         int k_old = -1;
         if (!cand) {
             k_old = s.slot_of_uid[uid];
-            if (s.rec[(size_t)(Ly::SC + F_N) * st + k_old] == 1.0) cand = true;  // the component would die
+            if (s.rec[(Ly::SC + F_N) * ST + k_old] == 1.0) cand = true;  // the component would die
         }
         if (!cand) {
-            double x[DP];
-            const double *xr = p.X + (size_t)i * DP;
-            if (DP >= 2) {
-#pragma unroll
-                for (int a = 0; a < DP; a += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(xr + a);
-                    x[a] = v.x; x[a + 1] = v.y;
-                }
-            } else {
-                x[0] = xr[0];
-            }
+            const double wref = p.log_alpha + c.lp;
+            // which entries of the row are stale: none, the two components of the last change, or all
+            int ka = -1, kb = -1;
+            bool all = true;
+            if (c.ver == ver && c.K == K) { all = false; }
+            else if (c.ver == ver - 1 && !sh.dirty_all && c.K <= K) { all = false; ka = sh.dirty_a; kb = sh.dirty_b; }
             bool ok = true;
-            for (int k = lane; k < K; k += 32) {
-                double w;
-                if (k == k_old) w = f_weight_own<DP>(s.rec + k, st, x, &ok);
-                else w = f_weight_other<DP>(s.rec + k, st, x);
-                wrow[k] = w;
+            if (all) {
+                for (int k = lane; k < K; k += 32) {
+                    const double e = f_eval_lane<DP, ST>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0);
+                    if (e != e) ok = false;
+                    ew[k] = e;
+                }
+            } else if (ka >= 0 || kb >= 0) {
+                const int k = (lane == 0) ? ka : ((lane == 1) ? kb : -1);
+                if (k >= 0) {
+                    const double e = f_eval_lane<DP, ST>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0);
+                    if (e != e) ok = false;
+                    ew[k] = e;
+                }
             }
-            if (lane == 0) wrow[K] = p.log_alpha + p.log_prior[i];
+            if (lane == 0) ew[K] = 1.0;
             ok = __all_sync(0xffffffffu, ok);
             __syncwarp();
+            c.ver = ok ? ver : -1;
+            c.K = K;
             if (!ok) {
                 cand = true;
             } else {
                 double mg;
-                bool bad;
-                const int k_new = f_warp_draw(wrow, K + 1, p.u[j], &mg, &bad);
-                if (k_new != k_old || bad) cand = true;
+                const int k_new = f_warp_pick(ew, K + 1, c.u, &mg);
+                if (k_new != k_old) cand = true;   // includes -2: the step redoes it in the log domain
                 else my_margin = fmin(my_margin, mg);
             }
             __syncwarp();
         }
         if (cand) {
-            if (lane == 0) atomicMin(first_slot, (unsigned long long)j);
+            double *mv = p.mvbuf + (size_t)gw * (DP + MV_EXTRA);
+            if (lane < DP) __stcg(mv + lane, xw[lane]);
+            if (lane == 0) {
+                __stcg(mv + DP, c.u);
+                __stcg(mv + DP + 1, c.lp);
+                __stcg(mv + DP + 2, __longlong_as_double(c.i));
+                __stcg(mv + DP + 3, __longlong_as_double((long long)uid));
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicMin(first_slot, ((unsigned long long)j << 12) | gw);
             break;
         }
     }
@@ -794,15 +905,22 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
 // the sweep kernel: cooperative grid, one CTA per SM
 // ---------------------------------------------------------------------------------------------
 template <int DP>
-__global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p) {
+__global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
     extern __shared__ __align__(16) double smem_raw[];
     using Ly = Lay<DP>;
-    const FSmem<DP> s = fast_carve<DP>(smem_raw, p);
+    constexpr int ST = Ly::KS;
+    // the out-of-line device functions take these by reference: keep one copy in shared memory, not one per thread
+    // in local memory
+    __shared__ Params p_sh;
+    __shared__ FSmem<DP> s_sh;
+    if (threadIdx.x == 0) { p_sh = p_in; s_sh = fast_carve<DP>(smem_raw, p_in); }
+    __syncthreads();
+    const Params &p = p_sh;
+    const FSmem<DP> &s = s_sh;
     FSh &sh = *s.sh;
     Ctl *ctl = p.ctl;
     const int tid = threadIdx.x;
     const bool cta0 = (blockIdx.x == 0);
-    const int st = p.KS;
 
     // ---- prologue: replicate the chain state ----
     if (tid == 0) {
@@ -816,6 +934,10 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p) {
         const double one = 1.0;
         sh.margin_bits = (unsigned long long)__double_as_longlong(one);
         sh.round = 0;
+        sh.k_new = 0; sh.need_explicit = 0; sh.explicit_done = 0; sh.refresh_a = 0; sh.refresh_b = 0;
+        sh.ver = 1; sh.dirty_a = sh.dirty_b = -1; sh.dirty_all = 1;
+        for (int t = 0; t < PH_COUNT; ++t) sh.prof[t] = 0;
+        sh.prof_last = clock64();
         sh.mode = (p.engine == 2) ? 1 : ((p.engine == 1) ? 0 : (p.init_gap >= GAP_TO_WIN ? 1 : 0));
         const uint32_t mb = smem_u32(&sh.mbar);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
@@ -834,9 +956,9 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p) {
     for (int e = tid; e < Ly::R; e += TF) s.prior[e] = __ldcg(p.recB_prior + e);
     __syncthreads();
     {
-        // records: one TMA bulk copy of the whole element-major table (cp.async.bulk + mbarrier complete_tx)
-        // whole table, rounded up to the 16-byte granule (the global buffer and the shared region are padded)
-        const uint32_t bytes = (uint32_t)(((size_t)Ly::R * st * sizeof(double) + 15) & ~(size_t)15);
+        // records: one TMA bulk copy of the whole element-major table (cp.async.bulk + mbarrier complete_tx),
+        // rounded up to the 16-byte granule (the global buffer and the shared region are padded)
+        const uint32_t bytes = (uint32_t)(((size_t)Ly::R * ST * sizeof(double) + 15) & ~(size_t)15);
         const uint32_t mb = smem_u32(&sh.mbar);
         if (tid == 0) {
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -866,6 +988,10 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p) {
     // no replica may still be reading the initial state when CTA 0 starts changing it
     f_grid_barrier(ctl);
 
+    WCache cache;
+    cache.j = -1; cache.i = 0; cache.uid = -1; cache.ver = -1; cache.K = 0; cache.u = 0.0; cache.lp = 0.0;
+    int seq = 0;
+
     // ---- main loop ----
     while (true) {
         const long long pos = sh.pos;
@@ -875,33 +1001,54 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p) {
         if (mode == 0) {
             const int nb = (int)min((long long)SEQ_BATCH, p.N - pos);
             const long long moves0 = sh.moves;
-            const int done = f_run<DP>(p, s, pos, nb);
+            __syncthreads();
+            const int done = f_run<DP>(p, s, pos, nb, seq);
             __syncthreads();
             if (tid == 0) {
                 const long long mv = sh.moves - moves0;
                 sh.gap = 0.5 * sh.gap + 0.5 * (double)nb / ((double)mv + 0.5);
                 sh.seq_data += done;
                 sh.pos = pos + done;
+                sh.dirty_all = 1;   // several changes since the evaluators last looked
                 if (p.engine == 0 && sh.gap >= GAP_TO_WIN) sh.mode = 1;
             }
         } else {
             const unsigned int r = sh.round;
             unsigned long long *slot = &ctl->first3[r % 3u];
-            if (cta0 && tid == 0) __stcg(&ctl->first3[(r + 1u) % 3u], (unsigned long long)POS_INF);
+            if (cta0 && tid == 0) __stcg(&ctl->first3[(r + 1u) % 3u], ~0ULL >> 1);
             const int K = sh.K;
-            const long long wcap = (long long)gridDim.x * NWARP * WIN_PASSES_MAX;
-            long long win = (long long)fmin(fmax(3.0 * sh.gap, (double)gridDim.x), (double)wcap);
+            const long long G = gridDim.x;
+            const long long wcap = G * NWARP * WIN_PASSES_MAX;
+            long long win = (long long)fmin(2.0 * sh.gap, (double)wcap);
+            win = ((win + G - 1) / G) * G;   // whole rows of one datum per SM
+            if (win < G) win = G;
             if (win > p.N - pos) win = p.N - pos;
-            f_window_eval<DP>(p, s, pos, win, K, slot);
+            F_PROF(PH_HEAD);
+            f_window_eval<DP>(p, s, pos, win, K, slot, cache);
+            __syncthreads();
+            F_PROF(PH_WINEVAL);
             f_grid_barrier(ctl);
-            const long long f = (long long)__ldcg(slot);
+            F_PROF(PH_BARRIER);
+            if (tid == 0 && cta0) sh.prof[PH_ROUNDS] += 1;
+            const unsigned long long fv = __ldcg(slot);
+            const long long f = (long long)(fv >> 12);
             const long long end = pos + win;
             if (f < end) {
+                // every CTA resolves the first candidate itself, from the inputs its evaluator published
+                const double *mv = p.mvbuf + (size_t)(fv & 4095ULL) * (DP + MV_EXTRA);
+                if (tid < DP) s.xb[tid] = __ldcg(mv + tid);
+                else if (tid == DP) s.ub[0] = __ldcg(mv + DP);
+                else if (tid == DP + 1) s.lpb[0] = __ldcg(mv + DP + 1);
+                else if (tid == DP + 2) s.ib[0] = __double_as_longlong(__ldcg(mv + DP + 2));
+                else if (tid == DP + 3) s.uidb[0] = (int)__double_as_longlong(__ldcg(mv + DP + 3));
                 if (tid == 0) { sh.evals += (f - pos) * (long long)K; sh.wasted += end - (f + 1); }
-                const int done = f_run<DP>(p, s, f, 1);
+                __syncthreads();
+                F_PROF(PH_STAGE);
+                seq += 1;
+                f_step<DP>(p, s, 0, seq);
                 __syncthreads();
                 if (tid == 0) {
-                    sh.pos = f + done;
+                    sh.pos = f + (sh.error ? 0 : 1);
                     sh.gap = 0.7 * sh.gap + 0.3 * (double)(f - pos + 1);
                 }
             } else if (tid == 0) {
@@ -926,7 +1073,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p) {
             __stcg(p.slot_of_uid + t, s.slot_of_uid[t]);
             __stcg(p.uid_of_slot + t, s.uid_of_slot[t]);
             __stcg(p.uid_free + t, s.uid_free[t]);
-            __stcg(p.counts + t, t < K ? (long long)s.rec[(size_t)(Ly::SC + F_N) * st + t] : 0LL);
+            __stcg(p.counts + t, t < K ? (long long)s.rec[(Ly::SC + F_N) * ST + t] : 0LL);
         }
         if (tid == 0) {
             __stcg(&ctl->K, K);
@@ -944,6 +1091,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p) {
             __stcg(&ctl->refreshes, __ldcg(&ctl->refreshes) + sh.refreshes);
             atomicMin(&ctl->margin_bits, sh.margin_bits);
             __stcg(&ctl->gap, sh.gap);
+            for (int t = 0; t < PH_COUNT; ++t) __stcg(&ctl->prof[t], sh.prof[t]);
         }
     }
 }
@@ -964,7 +1112,7 @@ template <int DP> __global__ void k_fast_prep(const Params p, int K, int *err) {
     bool ok;
     if (k < K) {
         ok = f_exact_record_warp<DP>(p, 0, p.num + (size_t)k * DP, p.S + (size_t)k * Ly::PP, (double)p.counts[k], nullptr, rc,
-                                     A, W, mm, p.recB + k, p.KS);
+                                     A, W, mm, p.recB + k, Ly::KS);
     } else {
         ok = f_exact_record_warp<DP>(p, 1, nullptr, nullptr, 0.0, nullptr, rc, A, W, mm, p.recB_prior, 1);
     }

@@ -39,3 +39,4 @@ for s in range(a.sweeps):
     st = ch.sweep(1.0, a.power if s > 0 else 1.0, order, None)
     dt = time.time() - t
     print("sweep %d: %s wall=%.3fs evals/s=%.3e" % (s, st.as_dict(), dt, st.evals / (st.device_ms * 1e-3)), flush=True)
+    print("   phases(cycles):", st.phases(), flush=True)
