@@ -47,8 +47,12 @@ __host__ __device__ __forceinline__ int row_idx(int a, int b) { return a * (a + 
 // control block (device global memory, one per handle)
 // ---------------------------------------------------------------------------------------------
 struct Ctl {
+    // the barrier words and each round slot sit on their own 128-byte lines: they are hammered by every CTA
     unsigned int bar_count;
+    unsigned int pad_a[31];
     unsigned int bar_gen;
+    unsigned int pad_b[31];
+    unsigned long long first3[3][16];  // per-round atomicMin targets of the fast engine (round r uses [r % 3][0])
     int K;
     int error;          // 0, or a BGMM_E* code
     long long pos;      // next scan position
@@ -63,8 +67,6 @@ struct Ctl {
     long long moves, births, deaths, evals, windows, seq_data, wasted;
     unsigned long long margin_bits;
     double gap;         // running estimate of the number of data between two movers
-    // fast engine (bgmm_fast.cuh)
-    unsigned long long first3[3];  // per-round atomicMin targets (round r uses slot r % 3)
     long long explicit_evals, refreshes;
     long long prof[16];            // phase clocks of CTA 0 (cycles), see bgmm_fast.cuh
 };

@@ -385,7 +385,7 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
         memset(&c, 0, sizeof(c));
         c.n_free = K_max;
         c.first = POS_INF;
-        c.first3[0] = c.first3[1] = c.first3[2] = (unsigned long long)POS_INF;
+        c.first3[0][0] = c.first3[1][0] = c.first3[2][0] = (unsigned long long)POS_INF;
         const double one = 1.0;
         memcpy(&c.margin_bits, &one, 8);
         CU(cudaMemcpy(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
@@ -491,7 +491,7 @@ int bgmm_set_assignments(bgmm_t *h, const int64_t *z) {
     Ctl c;
     memset(&c, 0, sizeof(c));
     c.K = K0; c.n_free = n_free; c.first = POS_INF;
-    c.first3[0] = c.first3[1] = c.first3[2] = (unsigned long long)POS_INF;
+    c.first3[0][0] = c.first3[1][0] = c.first3[2][0] = (unsigned long long)POS_INF;
     const double one = 1.0;
     memcpy(&c.margin_bits, &one, 8);
     CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
@@ -529,7 +529,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     const double one = 1.0;
     memcpy(&c.margin_bits, &one, 8);
     c.error = 0; c.bar_count = 0; c.pos = 0; c.win = 0; c.first = POS_INF; c.n_dirty = 0;
-    c.first3[0] = c.first3[1] = c.first3[2] = (unsigned long long)POS_INF;
+    c.first3[0][0] = c.first3[1][0] = c.first3[2][0] = (unsigned long long)POS_INF;
     CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
     Params p = make_params(h);
     p.order = d_order; p.u = d_u;

@@ -36,10 +36,11 @@ constexpr int NB_MAX = 6;             // weights per lane in the draw: supports 
 constexpr int E_NEED_GENERIC = 1;     // internal: a birth would exceed the resident capacity -> generic engine
 constexpr double GAP_TO_WIN = 6.0, GAP_TO_SEQ = 3.0;
 constexpr int WIN_PASSES_MAX = 8;
-constexpr int MV_EXTRA = 4;           // mover slot: x[DP], u, log prior, i, uid
+constexpr int MV_EXTRA = 5;           // mover slot: x[DP], u, log prior, i, uid, drawn component (-1: full step)
 // phase clocks (CTA 0, thread 0; cycles): reported through bgmm_sweep_stats.phase_cycles
 enum { PH_STAGE = 0, PH_HEAD, PH_EVAL, PH_DRAW, PH_UPDATE, PH_SCALARS, PH_WINEVAL, PH_BARRIER, PH_RARE, PH_STEPS, PH_MOVES,
        PH_ROUNDS, PH_COUNT = 16 };
+#ifdef BGMM_PROFILE
 #define F_PROF(slot)                                                  \
     do {                                                              \
         if (threadIdx.x == 0 && blockIdx.x == 0) {                    \
@@ -48,6 +49,11 @@ enum { PH_STAGE = 0, PH_HEAD, PH_EVAL, PH_DRAW, PH_UPDATE, PH_SCALARS, PH_WINEVA
             s.sh->prof_last = t_;                                     \
         }                                                             \
     } while (0)
+#define F_COUNT(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) s.sh->prof[slot] += 1; } while (0)
+#else
+#define F_PROF(slot) do { } while (0)
+#define F_COUNT(slot) do { } while (0)
+#endif
 
 // Everything in a record that depends on the component's count n alone comes from the count table
 // Params::ntab (8 doubles per n, built once per chain / per power by k_fast_ntab):
@@ -106,6 +112,7 @@ static __device__ __noinline__ void f_grid_barrier(Ctl *c) {
 }
 
 struct FSh {
+    unsigned long long fv;   // the round's first-candidate word, read once per CTA (f_round_barrier)
     // replicated chain state
     int K, n_free, error, mode;
     long long pos;
@@ -121,6 +128,30 @@ struct FSh {
     unsigned long long mbar;
     long long prof[PH_COUNT], prof_last;
 };
+
+// the per-round barrier: as f_grid_barrier, and thread 0 reads the round's first-candidate word once for the CTA
+// (one request per CTA instead of one per warp on a single L2 line)
+static __device__ __noinline__ void f_round_barrier(Ctl *c, const unsigned long long *slot, unsigned long long *fv_out) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int gen = ld_acquire_u32(&c->bar_gen);
+        __threadfence();
+        unsigned int prev = atomicAdd(&c->bar_count, 1u);
+        if (prev == gridDim.x - 1) {
+            c->bar_count = 0;
+            __threadfence();
+            st_release_u32(&c->bar_gen, gen + 1);
+        } else {
+            const long long t0 = clock64();
+            while (ld_acquire_u32(&c->bar_gen) == gen) {
+                if (clock64() - t0 > 8000000000LL) __trap();
+            }
+        }
+        __threadfence();
+        *fv_out = __ldcg(slot);
+    }
+    __syncthreads();
+}
 
 template <int DP> struct FSmem {
     double *rec;      // R * KS
@@ -630,6 +661,85 @@ __device__ __noinline__ void f_refresh(const Params &p, const FSmem<DP> &s, int 
     f_grid_barrier(p.ctl);
 }
 
+// a new component opens in slot K, initialised with the prior (gaussian_components.py:161-164).  false: error set
+template <int DP> __device__ __noinline__ bool f_open_component(const Params &p, const FSmem<DP> &s, int K) {
+    using Ly = Lay<DP>;
+    FSh &sh = *s.sh;
+    const int tid = threadIdx.x;
+    if (K >= p.K_max || K >= Ly::KCAP) {
+        // K_max: the reference would raise IndexError.  Resident capacity: nothing has been changed for this datum
+        // yet, the generic engine redoes it.
+        __syncthreads();
+        if (tid == 0) {
+            if (K >= p.K_max) sh.error = -3;
+            else { sh.error = E_NEED_GENERIC; sh.evals -= K; }
+        }
+        __syncthreads();
+        return false;
+    }
+    for (int e = tid; e < Ly::R; e += TF) s.rec[(size_t)e * Ly::KS + K] = s.prior[e];
+    if (tid == 0) {
+        const int nuid = s.uid_free[sh.n_free - 1];
+        sh.n_free -= 1;
+        s.uid_of_slot[K] = nuid;
+        s.slot_of_uid[nuid] = K;
+        sh.K = K + 1;
+        sh.births += 1;
+    }
+    __syncthreads();
+    return true;
+}
+
+// the state change of a move (whole CTA): the datum leaves k_old (if remove_now) and joins k_new
+template <int DP>
+__device__ __noinline__ void f_move_phase(const Params &p, const FSmem<DP> &s, int jj, int k_old, int k_new,
+                                          bool remove_now, bool birth, bool expl, bool died, int seq) {
+    using Ly = Lay<DP>;
+    constexpr int ST = Ly::KS;
+    FSh &sh = *s.sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *xs = s.xb + jj * DP;
+    if (warp == 0) {
+        if (remove_now) {
+            if (expl) {
+                for (int e = lane; e < Ly::R; e += 32) s.rec[(size_t)e * ST + k_old] = s.tmprec[e];
+            } else {
+                f_rank_one_warp<DP>(p, s, k_old, -1, xs, 0, seq);
+            }
+        }
+    } else if (warp == 1) {
+        f_rank_one_warp<DP>(p, s, k_new, +1, xs, 1, seq);
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // what this step changed, for the evaluators' cached rows
+            sh.ver += 1;
+            sh.dirty_a = remove_now ? k_old : -1;
+            sh.dirty_b = k_new;
+            sh.dirty_all = (died || expl) ? 1 : 0;
+        }
+    } else if (blockIdx.x == 0 && warp >= 8) {
+        // CTA 0: the bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition)
+        if (warp < 12) {
+            if (remove_now) f_stats_axpy<DP>(p, s.rc, k_old, xs, -1, 0, tid - 256, 128);
+        } else {
+            f_stats_axpy<DP>(p, s.rc, k_new, xs, +1, birth ? 1 : 0, tid - 384, 128);
+            if (tid == 384) __stcg(p.z_out + s.ib[jj], s.uid_of_slot[k_new]);  // replicas keep reading the input labels
+        }
+    }
+    __syncthreads();
+    F_PROF(PH_UPDATE);
+    F_COUNT(PH_MOVES);
+    const bool ra = (sh.refresh_a == seq), rb = (sh.refresh_b == seq);
+    if (ra || rb) {
+        const double n_a = ra ? s.rec[(Ly::SC + F_N) * ST + k_old] : 0.0;
+        const double n_b = s.rec[(Ly::SC + F_N) * ST + k_new];
+        f_refresh<DP>(p, s, ra ? k_old : -1, n_a, rb ? k_new : -1, n_b);
+        if (tid == 0) sh.dirty_all = 1;
+        __syncthreads();
+        F_PROF(PH_RARE);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Resolve ONE datum (whole CTA, every CTA identically).  Inputs in the staging buffers at index jj; seq is a
 // per-step sequence number (> 0) used to tag the rare-path flags so they never need resetting.
@@ -691,7 +801,7 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
     __syncthreads();
     if (sh.k_new == -2) f_log_domain_draw<DP>(p, s, K, k_old, own_live, expl, xs, wref, s.ub[jj], ew);
     F_PROF(PH_DRAW);
-    if (tid == 0 && cta0) sh.prof[PH_STEPS] += 1;
+    F_COUNT(PH_STEPS);
     if (sh.error) return;
     const int k_new = sh.k_new;
     if (k_new == k_old && !died) return;  // stay: nothing was touched (crpmm.py:82-85)
@@ -699,64 +809,9 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
     // phase C: the datum moves: add_item (gaussian_components.py:154-169)
     const bool birth = (k_new == K);
     if (birth) {
-        if (K >= p.K_max) { __syncthreads(); if (tid == 0) sh.error = -3; __syncthreads(); return; }
-        if (K >= Ly::KCAP) {  // nothing has been changed for this datum yet: the generic engine redoes it
-            __syncthreads();
-            if (tid == 0) { sh.error = E_NEED_GENERIC; sh.evals -= K; }
-            __syncthreads();
-            return;
-        }
-        for (int e = tid; e < Ly::R; e += TF) s.rec[(size_t)e * ST + K] = s.prior[e];
-        if (tid == 0) {
-            const int nuid = s.uid_free[sh.n_free - 1];
-            sh.n_free -= 1;
-            s.uid_of_slot[K] = nuid;
-            s.slot_of_uid[nuid] = K;
-            sh.K = K + 1;
-            sh.births += 1;
-        }
-        __syncthreads();
+        if (!f_open_component<DP>(p, s, K)) return;
     }
-    const bool remove_now = own_live;
-    if (warp == 0) {
-        if (remove_now) {
-            if (expl) {
-                for (int e = lane; e < Ly::R; e += 32) s.rec[(size_t)e * ST + k_old] = s.tmprec[e];
-            } else {
-                f_rank_one_warp<DP>(p, s, k_old, -1, xs, 0, seq);
-            }
-        }
-    } else if (warp == 1) {
-        f_rank_one_warp<DP>(p, s, k_new, +1, xs, 1, seq);
-    } else if (warp == 2) {
-        if (lane == 0) {
-            // what this step changed, for the evaluators' cached rows
-            sh.ver += 1;
-            sh.dirty_a = remove_now ? k_old : -1;
-            sh.dirty_b = k_new;
-            sh.dirty_all = (died || expl) ? 1 : 0;
-        }
-    } else if (cta0 && warp >= 8) {
-        // CTA 0: the bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition)
-        if (warp < 12) {
-            if (remove_now) f_stats_axpy<DP>(p, s.rc, k_old, xs, -1, 0, tid - 256, 128);
-        } else {
-            f_stats_axpy<DP>(p, s.rc, k_new, xs, +1, birth ? 1 : 0, tid - 384, 128);
-            if (tid == 384) __stcg(p.z_out + s.ib[jj], s.uid_of_slot[k_new]);  // replicas keep reading the input labels
-        }
-    }
-    __syncthreads();
-    F_PROF(PH_UPDATE);
-    if (tid == 0 && cta0) sh.prof[PH_MOVES] += 1;
-    const bool ra = (sh.refresh_a == seq), rb = (sh.refresh_b == seq);
-    if (ra || rb) {
-        const double n_a = ra ? s.rec[(Ly::SC + F_N) * ST + k_old] : 0.0;
-        const double n_b = s.rec[(Ly::SC + F_N) * ST + k_new];
-        f_refresh<DP>(p, s, ra ? k_old : -1, n_a, rb ? k_new : -1, n_b);
-        if (tid == 0) sh.dirty_all = 1;
-        __syncthreads();
-        F_PROF(PH_RARE);
-    }
+    f_move_phase<DP>(p, s, jj, k_old, k_new, own_live, birth, expl, died, seq);
 }
 
 // stage `nb` data starting at scan position pos into the buffers, then resolve them in order
@@ -805,7 +860,7 @@ struct WCache {
 
 template <int DP>
 __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos, long long win, int K,
-                              unsigned long long *first_slot, WCache &c) {
+                              unsigned long long *first_slot, WCache &c, double &my_margin) {
     using Ly = Lay<DP>;
     constexpr int ST = Ly::KS;
     const FSh &sh = *s.sh;
@@ -820,12 +875,16 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
     long long j = pos - (pos % stride) + own;
     if (j < pos) j += stride;
     const int ver = sh.ver;
-    double my_margin = 1.0;
+    bool first_pass = true;
     for (; j < end; j += stride) {
-        long long known = 0;
-        if (lane == 0) known = (long long)(__ldcg(first_slot) >> 12);
-        known = __shfl_sync(0xffffffffu, known, 0);
-        if (known < j) break;  // an earlier candidate is already known: this datum would be redone
+        if (!first_pass) {
+            // later passes of a long window: stop once an earlier candidate is known (this datum would be redone)
+            long long known = 0;
+            if (lane == 0) known = (long long)(__ldcg(first_slot) >> 12);
+            known = __shfl_sync(0xffffffffu, known, 0);
+            if (known < j) break;
+        }
+        first_pass = false;
         if (c.j != j) {
             const long long i = p.order ? p.order[j] : j;
             c.j = j; c.i = i; c.ver = -1;
@@ -838,7 +897,7 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
         }
         const int uid = c.uid;
         bool cand = (uid < 0);
-        int k_old = -1;
+        int k_old = -1, drawn = -1;
         if (!cand) {
             k_old = s.slot_of_uid[uid];
             if (s.rec[(Ly::SC + F_N) * ST + k_old] == 1.0) cand = true;  // the component would die
@@ -875,8 +934,14 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
             } else {
                 double mg;
                 const int k_new = f_warp_pick(ew, K + 1, c.u, &mg);
-                if (k_new != k_old) cand = true;   // includes -2: the step redoes it in the log domain
-                else my_margin = fmin(my_margin, mg);
+                if (k_new != k_old) {
+                    cand = true;   // includes -2: the step redoes it in the log domain
+                    // a plain move between two live components needs no second evaluation if it turns out to be
+                    // the first candidate: every datum in front of it stayed, so the records it saw are current
+                    if (k_new >= 0 && k_new < K) { drawn = k_new; my_margin = fmin(my_margin, mg); }
+                } else {
+                    my_margin = fmin(my_margin, mg);
+                }
             }
             __syncwarp();
         }
@@ -888,16 +953,13 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
                 __stcg(mv + DP + 1, c.lp);
                 __stcg(mv + DP + 2, __longlong_as_double(c.i));
                 __stcg(mv + DP + 3, __longlong_as_double((long long)uid));
+                __stcg(mv + DP + 4, __longlong_as_double((long long)drawn));
             }
             __threadfence();
             __syncwarp();
             if (lane == 0) atomicMin(first_slot, ((unsigned long long)j << 12) | gw);
             break;
         }
-    }
-    if (lane == 0 && my_margin < 1.0) {
-        // committed and discarded evaluations alike: a lower bound of the chain's true minimum margin
-        atomicMin(&p.ctl->margin_bits, (unsigned long long)__double_as_longlong(my_margin));
     }
 }
 
@@ -991,6 +1053,9 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
     WCache cache;
     cache.j = -1; cache.i = 0; cache.uid = -1; cache.ver = -1; cache.K = 0; cache.u = 0.0; cache.lp = 0.0;
     int seq = 0;
+    // minimum margin over this warp's window evaluations (committed and discarded alike: a lower bound of the
+    // chain's true minimum margin); folded into the control block once, at the end
+    double win_margin = 1.0;
 
     // ---- main loop ----
     while (true) {
@@ -1014,8 +1079,8 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             }
         } else {
             const unsigned int r = sh.round;
-            unsigned long long *slot = &ctl->first3[r % 3u];
-            if (cta0 && tid == 0) __stcg(&ctl->first3[(r + 1u) % 3u], ~0ULL >> 1);
+            unsigned long long *slot = &ctl->first3[r % 3u][0];
+            if (cta0 && tid == 0) __stcg(&ctl->first3[(r + 1u) % 3u][0], ~0ULL >> 1);
             const int K = sh.K;
             const long long G = gridDim.x;
             const long long wcap = G * NWARP * WIN_PASSES_MAX;
@@ -1024,28 +1089,39 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             if (win < G) win = G;
             if (win > p.N - pos) win = p.N - pos;
             F_PROF(PH_HEAD);
-            f_window_eval<DP>(p, s, pos, win, K, slot, cache);
+            f_window_eval<DP>(p, s, pos, win, K, slot, cache, win_margin);
             __syncthreads();
             F_PROF(PH_WINEVAL);
-            f_grid_barrier(ctl);
+            f_round_barrier(ctl, slot, &sh.fv);
             F_PROF(PH_BARRIER);
-            if (tid == 0 && cta0) sh.prof[PH_ROUNDS] += 1;
-            const unsigned long long fv = __ldcg(slot);
+            F_COUNT(PH_ROUNDS);
+            const unsigned long long fv = sh.fv;
             const long long f = (long long)(fv >> 12);
             const long long end = pos + win;
             if (f < end) {
                 // every CTA resolves the first candidate itself, from the inputs its evaluator published
                 const double *mv = p.mvbuf + (size_t)(fv & 4095ULL) * (DP + MV_EXTRA);
-                if (tid < DP) s.xb[tid] = __ldcg(mv + tid);
-                else if (tid == DP) s.ub[0] = __ldcg(mv + DP);
-                else if (tid == DP + 1) s.lpb[0] = __ldcg(mv + DP + 1);
-                else if (tid == DP + 2) s.ib[0] = __double_as_longlong(__ldcg(mv + DP + 2));
-                else if (tid == DP + 3) s.uidb[0] = (int)__double_as_longlong(__ldcg(mv + DP + 3));
+                if (tid < DP + MV_EXTRA) {
+                    const double v = __ldcg(mv + tid);
+                    if (tid < DP) s.xb[tid] = v;
+                    else if (tid == DP) s.ub[0] = v;
+                    else if (tid == DP + 1) s.lpb[0] = v;
+                    else if (tid == DP + 2) s.ib[0] = __double_as_longlong(v);
+                    else if (tid == DP + 3) s.uidb[0] = (int)__double_as_longlong(v);
+                    else sh.k_new = (int)__double_as_longlong(v);
+                }
                 if (tid == 0) { sh.evals += (f - pos) * (long long)K; sh.wasted += end - (f + 1); }
                 __syncthreads();
+                const int drawn = sh.k_new;
                 F_PROF(PH_STAGE);
                 seq += 1;
-                f_step<DP>(p, s, 0, seq);
+                if (drawn >= 0) {
+                    // a plain move, already drawn by its evaluator against the current records
+                    if (tid == 0) sh.evals += K;
+                    f_move_phase<DP>(p, s, 0, s.slot_of_uid[s.uidb[0]], drawn, true, false, false, false, seq);
+                } else {
+                    f_step<DP>(p, s, 0, seq);
+                }
                 __syncthreads();
                 if (tid == 0) {
                     sh.pos = f + (sh.error ? 0 : 1);
@@ -1067,6 +1143,8 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
 
     // ---- epilogue: CTA 0 publishes the chain state ----
     __syncthreads();
+    if ((tid & 31) == 0 && win_margin < 1.0)
+        atomicMin(&ctl->margin_bits, (unsigned long long)__double_as_longlong(win_margin));
     if (cta0) {
         const int K = sh.K;
         for (int t = tid; t < p.K_max; t += TF) {
