@@ -353,8 +353,9 @@ def run_ours(a):
     d_o = [torch.from_numpy(o).to(dev) if o is not None else None for o in orders]
     d_u = [torch.from_numpy(u).to(dev) for u in unis]
     chain.set_assignments(z0)
+    warm = []
     for s in range(W):
-        chain.sweep_dev(1.0, pw(s), 0 if d_o[s] is None else d_o[s].data_ptr(), d_u[s].data_ptr())
+        warm.append(chain.sweep_dev(1.0, pw(s), 0 if d_o[s] is None else d_o[s].data_ptr(), d_u[s].data_ptr()))
     sync_all()
     sampler_thread = ClockSampler(local_rank)
     if rank == 0:
@@ -371,7 +372,8 @@ def run_ours(a):
     ms = reduce_max(e0.elapsed_time(e1))
     evals = float(sum(st.evals for st in stats))
     total_evals = reduce_sum(evals)
-    kernel_ms = sum(st.device_ms for st in stats)          # CUDA events around the sweep kernel, on its stream
+    kernel_ms = sum(st.sweep_kernel_ms for st in stats)    # CUDA events around the sweep kernel alone, on its stream
+    launches = int(sum(st.launches for st in stats))
     same = bool((chain.assignments() == z_e2e).all())      # both arms walked the same chain
 
     # gather of per-rank assignments at the end (NCCL over NVLink), outside the timed steps
@@ -410,16 +412,21 @@ def run_ours(a):
         "sweeps_per_s": world * K / (ms * 1e-3),
         "e2e": {"value": e2e_total_evals / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K, "same_chain_as_value_arm": same},
-        "gpu_launches": K,
+        "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(wl), "peak_source": peak_src, "kernel": "k_sweep",
+                     "traffic": ncu_traffic(wl), "peak_source": peak_src, "kernel": "k_fast_sweep<16> (one launch = one sweep)" if (cov == "full" and D <= 16) else "k_sweep",
                      "algorithmic_bytes_per_eval": b_eval, "algorithmic_bytes_per_datum": b_datum,
                      "kernel_ms_per_launch": kernel_ms / K,
                      "fp64_tflops": evals * 2 * flops_eval / (kernel_ms * 1e-3) / 1e12,
                      "note": "algorithmic bytes per SURVEY.md 8(d): one sufficient-statistic record per eval; the "
-                             "records are staged once per CTA in shared memory and reused across data, so DRAM "
-                             "traffic is far below this figure (see DESIGN.md)"},
+                             "records live in every CTA's shared memory and are reused across data, so DRAM "
+                             "traffic is far below this figure and the sweep is bound by the sequential "
+                             "dependency (one window round per mover), not by HBM (see DESIGN.md 4)"},
+        "cold_chain": {"note": "the %d untimed warm-up sweeps from the rand initial state, device-resident arm" % W,
+                       "ms": [round(st.device_ms, 3) for st in warm], "moves": [int(st.moves) for st in warm],
+                       "K_live": [int(st.K) for st in warm],
+                       "evals_per_s": [st.evals / (st.device_ms * 1e-3) for st in warm]},
         "engine": {"windows": [int(st.windows) for st in stats], "seq_data": [int(st.seq_data) for st in stats],
                    "wasted": [int(st.wasted) for st in stats], "min_margin": min(st.min_margin for st in stats)},
     }

@@ -55,6 +55,8 @@ typedef struct {
     int64_t refreshes;      /* records rebuilt from the statistics for drift control (engine diagnostic)      */
     int64_t generic_from;   /* scan position the generic engine took over at, or -1 (engine diagnostic)       */
     int64_t phase_cycles[16]; /* SM cycles CTA 0 spent per engine phase in the last sweep (engine diagnostic)   */
+    int64_t launches;         /* kernels launched by this call                                                  */
+    double sweep_kernel_ms;   /* CUDA-event time of the sweep kernel alone (device_ms also covers record set-up) */
 } bgmm_sweep_stats;
 
 const char *bgmm_version(void);

@@ -27,7 +27,8 @@ class SweepStats(C.Structure):
     _fields_ = [("K", C.c_int64), ("moves", C.c_int64), ("births", C.c_int64), ("deaths", C.c_int64),
                 ("evals", C.c_int64), ("windows", C.c_int64), ("seq_data", C.c_int64), ("wasted", C.c_int64),
                 ("min_margin", C.c_double), ("device_ms", C.c_double), ("explicit_evals", C.c_int64),
-                ("refreshes", C.c_int64), ("generic_from", C.c_int64), ("phase_cycles", C.c_int64 * 16)]
+                ("refreshes", C.c_int64), ("generic_from", C.c_int64), ("phase_cycles", C.c_int64 * 16),
+                ("launches", C.c_int64), ("sweep_kernel_ms", C.c_double)]
 
     PHASES = ("stage", "head", "eval", "draw", "update", "scalars", "wineval", "barrier", "rare", "steps", "moves",
               "rounds")

@@ -208,6 +208,8 @@ static void free_all(bgmm_handle *h) {
     cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf); cudaFree(h->d_ntab);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->ev3) cudaEventDestroy(h->ev3);
 }
 
 static int check_dev_err(bgmm_handle *h, const char *what) {
@@ -345,6 +347,8 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
 #undef ALLOC
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
+    CU(cudaEventCreate(&h->ev2));
+    CU(cudaEventCreate(&h->ev3));
 
     // uploads
     if (DP == D) {
@@ -513,8 +517,10 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     if (!(alpha > 0.0)) return fail(BGMM_EINVAL, "alpha must be > 0");
     if (!(power > 0.0)) return fail(BGMM_EINVAL, "power must be > 0");
     cudaStream_t st = h->stream;
+    h->launches = 0;
     if (!d_u) {
         const int T = 256;
+        h->launches += 1;
         k_philox<<<(unsigned)((h->N + T - 1) / T), T, 0, st>>>(h->d_u, h->N, h->seed, (unsigned long long)h->sweep_index);
         CU(cudaGetLastError());
         d_u = h->d_u;
@@ -543,14 +549,19 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         // the replicas read the labels as they were at the start of the sweep; CTA 0 writes the other copy
         CU(cudaMemcpyAsync(h->d_z2, h->d_z, sizeof(int) * (size_t)h->N, cudaMemcpyDeviceToDevice, st));
         if (int rc = h->ops->fast_prep(h, p, c.K)) return rc;
+        CU(cudaEventRecord(h->ev2, st));
         if (int rc = h->ops->fast_sweep(h, p)) return rc;
+        CU(cudaEventRecord(h->ev3, st));
+        h->launches += 1;
         std::swap(h->d_z, h->d_z2);
         p.z_uid = h->d_z; p.z_out = h->d_z2;
         CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         // the generic engine's (Cholesky) records, used by the auxiliary entry points, follow from the statistics
-        if (c.K > 0)
+        if (c.K > 0) {
             if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
+            h->launches += 1;
+        }
         if (c.error == fast::E_NEED_GENERIC) {  // more live components than fit in shared memory: continue generically
             generic_from = c.pos;
             c.error = 0; c.bar_count = 0;
@@ -558,15 +569,20 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
             fast = false;
         }
     }
+    const bool ran_fast = fast || generic_from >= 0;
     if (!fast) {
         p.start_pos = generic_from < 0 ? 0 : generic_from;
+        if (!ran_fast) CU(cudaEventRecord(h->ev2, st));
         if (int rc = h->ops->sweep(h, p)) return rc;
+        if (!ran_fast) CU(cudaEventRecord(h->ev3, st));
+        h->launches += 1;
     }
     CU(cudaEventRecord(h->ev1, st));
     CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    float ms = 0.f;
+    float ms = 0.f, ms_k = 0.f;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    CU(cudaEventElapsedTime(&ms_k, h->ev2, h->ev3));
     h->K = c.K;
     h->sweep_index += 1;
     h->last_gap = (double)h->N / (double)(c.moves + 1);
@@ -577,6 +593,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         out->device_ms = ms;
         out->explicit_evals = c.explicit_evals; out->refreshes = c.refreshes; out->generic_from = generic_from;
         for (int t = 0; t < 16; ++t) out->phase_cycles[t] = c.prof[t];
+        out->launches = h->launches; out->sweep_kernel_ms = ms_k;
     }
     if (c.error == BGMM_EKMAX) return fail(BGMM_EKMAX, "a new component would exceed K_max (the reference raises IndexError)");
     if (c.error != 0) return fail(c.error, "sweep: non-finite weights or covariance not positive definite");
