@@ -113,6 +113,7 @@ static __device__ __noinline__ void f_grid_barrier(Ctl *c) {
 
 struct FSh {
     unsigned long long fv;   // the round's first-candidate word, read once per CTA (f_round_barrier)
+    long long win;           // length of the next window (set by thread 0 with the state update)
     // replicated chain state
     int K, n_free, error, mode;
     long long pos;
@@ -269,6 +270,8 @@ template <int DP, int ST>
 __device__ __noinline__ double f_eval_lane(const double *__restrict__ col, const double *__restrict__ x, int own,
                                            double wref, int want_log) {
     using Ly = Lay<DP>;
+    // note: operands stay generic pointers on purpose.  Passing shared-window offsets (true LDS) was measured 15-40%
+    // slower: the compiler then schedules each load right before its use instead of hoisting the batch.
     double d[DP];
 #pragma unroll
     for (int a = 0; a < DP; ++a) d[a] = col[(Ly::MU + a) * ST] - x[a];
@@ -851,6 +854,7 @@ __device__ int f_run(const Params &p, const FSmem<DP> &s, long long pos, int nb,
 // atomicMin of (position << 12 | global warp id).
 // ---------------------------------------------------------------------------------------------
 struct WCache {
+    long long nj;     // first scan position owned by this warp that has not been passed yet
     long long j, i;   // scan position / datum held (-1: none)
     int uid;
     int ver;          // record version the row ew[] was evaluated at (-1: no row)
@@ -869,11 +873,10 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
     const long long end = pos + win;
     double *ew = s.ew + (size_t)warp * Ly::WS;
     double *xw = s.xw + (size_t)warp * DP;
-    const long long stride = G * NWARP;
-    const long long own = (long long)blockIdx.x + G * warp;  // j % stride == own
+    const long long stride = G * NWARP;   // this warp owns the positions congruent to blockIdx.x + G * warp
     const unsigned long long gw = (unsigned long long)(blockIdx.x * NWARP + warp);
-    long long j = pos - (pos % stride) + own;
-    if (j < pos) j += stride;
+    while (c.nj < pos) c.nj += stride;
+    long long j = c.nj;
     const int ver = sh.ver;
     bool first_pass = true;
     for (; j < end; j += stride) {
@@ -963,6 +966,17 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
     }
 }
 
+// length of the next window: about twice the running gap between movers, whole rows of one datum per SM
+__device__ __forceinline__ long long f_next_window(double gap, long long pos, long long N) {
+    const long long G = gridDim.x;
+    const long long wcap = G * NWARP * WIN_PASSES_MAX;
+    long long win = (long long)fmin(2.0 * gap, (double)wcap);
+    win = ((win + G - 1) / G) * G;
+    if (win < G) win = G;
+    if (win > N - pos) win = N - pos;
+    return win;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the sweep kernel: cooperative grid, one CTA per SM
 // ---------------------------------------------------------------------------------------------
@@ -1001,6 +1015,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
         for (int t = 0; t < PH_COUNT; ++t) sh.prof[t] = 0;
         sh.prof_last = clock64();
         sh.mode = (p.engine == 2) ? 1 : ((p.engine == 1) ? 0 : (p.init_gap >= GAP_TO_WIN ? 1 : 0));
+        sh.win = f_next_window(p.init_gap, p.start_pos, p.N);
         const uint32_t mb = smem_u32(&sh.mbar);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1051,6 +1066,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
     f_grid_barrier(ctl);
 
     WCache cache;
+    cache.nj = (long long)blockIdx.x + (long long)gridDim.x * (tid >> 5);
     cache.j = -1; cache.i = 0; cache.uid = -1; cache.ver = -1; cache.K = 0; cache.u = 0.0; cache.lp = 0.0;
     int seq = 0;
     // minimum margin over this warp's window evaluations (committed and discarded alike: a lower bound of the
@@ -1076,18 +1092,14 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
                 sh.pos = pos + done;
                 sh.dirty_all = 1;   // several changes since the evaluators last looked
                 if (p.engine == 0 && sh.gap >= GAP_TO_WIN) sh.mode = 1;
+                sh.win = f_next_window(sh.gap, sh.pos, p.N);
             }
         } else {
             const unsigned int r = sh.round;
             unsigned long long *slot = &ctl->first3[r % 3u][0];
             if (cta0 && tid == 0) __stcg(&ctl->first3[(r + 1u) % 3u][0], ~0ULL >> 1);
             const int K = sh.K;
-            const long long G = gridDim.x;
-            const long long wcap = G * NWARP * WIN_PASSES_MAX;
-            long long win = (long long)fmin(2.0 * sh.gap, (double)wcap);
-            win = ((win + G - 1) / G) * G;   // whole rows of one datum per SM
-            if (win < G) win = G;
-            if (win > p.N - pos) win = p.N - pos;
+            const long long win = sh.win;
             F_PROF(PH_HEAD);
             f_window_eval<DP>(p, s, pos, win, K, slot, cache, win_margin);
             __syncthreads();
@@ -1136,6 +1148,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
                 sh.windows += 1;
                 sh.round = r + 1u;
                 if (p.engine == 0 && sh.gap < GAP_TO_SEQ) sh.mode = 0;
+                sh.win = f_next_window(sh.gap, sh.pos, p.N);
             }
         }
         __syncthreads();
