@@ -36,6 +36,7 @@ constexpr int NB_MAX = 6;             // weights per lane in the draw: supports 
 constexpr int E_NEED_GENERIC = 1;     // internal: a birth would exceed the resident capacity -> generic engine
 constexpr double GAP_TO_WIN = 6.0, GAP_TO_SEQ = 3.0;
 constexpr int WIN_PASSES_MAX = 8;
+constexpr int DLOG = 16;              // versions of the dirty log (power of two)
 constexpr int MV_EXTRA = 5;           // mover slot: x[DP], u, log prior, i, uid, drawn component (-1: full step)
 // phase clocks (CTA 0, thread 0; cycles): reported through bgmm_sweep_stats.phase_cycles
 enum { PH_STAGE = 0, PH_HEAD, PH_EVAL, PH_DRAW, PH_UPDATE, PH_SCALARS, PH_WINEVAL, PH_BARRIER, PH_RARE, PH_STEPS, PH_MOVES,
@@ -123,8 +124,9 @@ struct FSh {
     // datum being resolved
     int k_new, need_explicit, explicit_done, refresh_a, refresh_b;
     // record version: bumped by every change of the records; the change from ver - 1 to ver touched only the
-    // components dirty_a / dirty_b (-1: none) unless dirty_all
-    int ver, dirty_a, dirty_b, dirty_all;
+    // components logged in dlog_a / dlog_b (-1: none) unless it is <= dall_ver
+    int ver, dall_ver;               // dall_ver: last version whose change was not confined to two components
+    int dlog_a[DLOG], dlog_b[DLOG];  // components touched by the change into version v, at index v % DLOG
     unsigned int round;
     unsigned long long mbar;
     long long prof[PH_COUNT], prof_last;
@@ -715,10 +717,11 @@ __device__ __noinline__ void f_move_phase(const Params &p, const FSmem<DP> &s, i
     } else if (warp == 2) {
         if (lane == 0) {
             // what this step changed, for the evaluators' cached rows
-            sh.ver += 1;
-            sh.dirty_a = remove_now ? k_old : -1;
-            sh.dirty_b = k_new;
-            sh.dirty_all = (died || expl) ? 1 : 0;
+            const int v = sh.ver + 1;
+            sh.ver = v;
+            sh.dlog_a[v & (DLOG - 1)] = remove_now ? k_old : -1;
+            sh.dlog_b[v & (DLOG - 1)] = k_new;
+            if (died || expl) sh.dall_ver = v;
         }
     } else if (blockIdx.x == 0 && warp >= 8) {
         // CTA 0: the bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition)
@@ -737,7 +740,7 @@ __device__ __noinline__ void f_move_phase(const Params &p, const FSmem<DP> &s, i
         const double n_a = ra ? s.rec[(Ly::SC + F_N) * ST + k_old] : 0.0;
         const double n_b = s.rec[(Ly::SC + F_N) * ST + k_new];
         f_refresh<DP>(p, s, ra ? k_old : -1, n_a, rb ? k_new : -1, n_b);
-        if (tid == 0) sh.dirty_all = 1;
+        if (tid == 0) sh.dall_ver = sh.ver;
         __syncthreads();
         F_PROF(PH_RARE);
     }
@@ -855,13 +858,62 @@ __device__ int f_run(const Params &p, const FSmem<DP> &s, long long pos, int nb,
 // ---------------------------------------------------------------------------------------------
 struct WCache {
     long long nj;     // first scan position owned by this warp that has not been passed yet
-    long long j, i;   // scan position / datum held (-1: none)
+    long long j, i;   // scan position being prepared / held (-1: none), its datum
     int uid;
-    int ver;          // record version the row ew[] was evaluated at (-1: no row)
-    int K;            // its length - 1
+    int stage;        // 0: nothing, 1: inputs loaded, 1 + c: c chunks of 32 components evaluated into the row ew[]
+    int ver;          // record version the row's oldest chunk was evaluated at
+    int K;            // live components when the row was started
     double u, lp;
 };
 
+// inputs of scan position c.j: datum index, label, uniform, cached log prior, and the row of X (into xw)
+template <int DP>
+__device__ __forceinline__ void f_load_inputs(const Params &p, WCache &c, double *xw) {
+    const int lane = threadIdx.x & 31;
+    const long long i = p.order ? p.order[c.j] : c.j;
+    c.i = i;
+    c.uid = __ldcg(p.z_uid + i);
+    c.u = p.u[c.j];
+    c.lp = p.log_prior[i];
+    __syncwarp();
+    if (lane < DP) xw[lane] = p.X[(size_t)i * DP + lane];
+    __syncwarp();
+    c.stage = 1;
+}
+
+// one chunk (32 components) of the row of exponentials of the held datum
+template <int DP>
+__device__ __forceinline__ void f_eval_chunk(const Params &p, const FSmem<DP> &s, WCache &c, int K, int ver,
+                                             const double *xw, double *ew) {
+    using Ly = Lay<DP>;
+    const int lane = threadIdx.x & 31;
+    const int chunk = c.stage - 1;
+    if (chunk == 0) { c.ver = ver; c.K = K; }
+    const int k = chunk * 32 + lane;
+    if (k < K) {
+        const int k_old = (c.uid >= 0) ? s.slot_of_uid[c.uid] : -1;
+        ew[k] = f_eval_lane<DP, Ly::KS>(s.rec + k, xw, k == k_old ? 1 : 0, p.log_alpha + c.lp, 0);
+    }
+    __syncwarp();
+    c.stage += 1;
+}
+
+// is the (partial) row still usable at record version `ver` with K live components?
+__device__ __forceinline__ bool f_row_usable(const FSh &sh, const WCache &c, int K, int ver) {
+    return c.stage >= 2 && c.K <= K && c.ver >= sh.dall_ver && ver - c.ver <= DLOG - 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One round of a warp's evaluator duty.  The warp owns the scan positions congruent to its global id; `c` holds
+// the next one (c.nj) in some stage of preparation.
+//  * not yet inside the window [pos, end): advance the preparation by ONE unit (load the inputs, or evaluate one
+//    chunk of 32 components), so that rows are ready rounds before the chain reaches them and no full evaluation
+//    sits on a round's critical path.  Rows go stale while they wait: the records of the components touched since
+//    are re-evaluated from the dirty log when the row is used (exact: all other entries saw unchanged records).
+//  * inside the window: finish the row, bring it up to date, draw.  A candidate (anything but a provable "stay")
+//    is published with its inputs and, for a plain move, the drawn component: mover slot of this warp, then
+//    atomicMin of (position << 12 | global warp id).
+// ---------------------------------------------------------------------------------------------
 template <int DP>
 __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos, long long win, int K,
                               unsigned long long *first_slot, WCache &c, double &my_margin) {
@@ -876,28 +928,34 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
     const long long stride = G * NWARP;   // this warp owns the positions congruent to blockIdx.x + G * warp
     const unsigned long long gw = (unsigned long long)(blockIdx.x * NWARP + warp);
     while (c.nj < pos) c.nj += stride;
-    long long j = c.nj;
     const int ver = sh.ver;
+    const int nch = (K + 31) >> 5;
+    if (c.j != c.nj) { c.j = c.nj; c.stage = 0; }
+    if (c.j >= end) {
+        // not needed this round: one unit of preparation
+        if (c.j < p.N) {
+            if (c.stage == 0) {
+                f_load_inputs<DP>(p, c, xw);
+            } else if (c.j - pos < 3 * win) {
+                // evaluate just in time: a row prepared too early would outlive the dirty log
+                if (c.stage >= 2 && !f_row_usable(sh, c, K, ver)) c.stage = 1;
+                if (c.stage - 1 < nch) f_eval_chunk<DP>(p, s, c, K, ver, xw, ew);
+            }
+        }
+        return;
+    }
     bool first_pass = true;
-    for (; j < end; j += stride) {
+    for (long long j = c.j; j < end; j += stride) {
         if (!first_pass) {
             // later passes of a long window: stop once an earlier candidate is known (this datum would be redone)
             long long known = 0;
             if (lane == 0) known = (long long)(__ldcg(first_slot) >> 12);
             known = __shfl_sync(0xffffffffu, known, 0);
             if (known < j) break;
+            c.j = j; c.stage = 0;
         }
         first_pass = false;
-        if (c.j != j) {
-            const long long i = p.order ? p.order[j] : j;
-            c.j = j; c.i = i; c.ver = -1;
-            c.uid = __ldcg(p.z_uid + i);
-            c.u = p.u[j];
-            c.lp = p.log_prior[i];
-            __syncwarp();
-            if (lane < DP) xw[lane] = p.X[(size_t)i * DP + lane];
-            __syncwarp();
-        }
+        if (c.stage == 0) f_load_inputs<DP>(p, c, xw);
         const int uid = c.uid;
         bool cand = (uid < 0);
         int k_old = -1, drawn = -1;
@@ -907,44 +965,31 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
         }
         if (!cand) {
             const double wref = p.log_alpha + c.lp;
-            // which entries of the row are stale: none, the two components of the last change, or all
-            int ka = -1, kb = -1;
-            bool all = true;
-            if (c.ver == ver && c.K == K) { all = false; }
-            else if (c.ver == ver - 1 && !sh.dirty_all && c.K <= K) { all = false; ka = sh.dirty_a; kb = sh.dirty_b; }
-            bool ok = true;
-            if (all) {
-                for (int k = lane; k < K; k += 32) {
-                    const double e = f_eval_lane<DP, ST>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0);
-                    if (e != e) ok = false;
-                    ew[k] = e;
-                }
-            } else if (ka >= 0 || kb >= 0) {
-                const int k = (lane == 0) ? ka : ((lane == 1) ? kb : -1);
-                if (k >= 0) {
-                    const double e = f_eval_lane<DP, ST>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0);
-                    if (e != e) ok = false;
-                    ew[k] = e;
+            if (c.stage >= 2 && !f_row_usable(sh, c, K, ver)) c.stage = 1;
+            const bool fresh = (c.stage == 1);
+            while (c.stage - 1 < nch) f_eval_chunk<DP>(p, s, c, K, ver, xw, ew);
+            if (!fresh && c.ver != ver) {
+                // entries of the components touched since the row's version (two per version, from the dirty log)
+                const int nd = 2 * (ver - c.ver);
+                if (lane < nd) {
+                    const int v = c.ver + 1 + (lane >> 1);
+                    const int k = (lane & 1) ? sh.dlog_b[v & (DLOG - 1)] : sh.dlog_a[v & (DLOG - 1)];
+                    if (k >= 0 && k < K) ew[k] = f_eval_lane<DP, ST>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0);
                 }
             }
             if (lane == 0) ew[K] = 1.0;
-            ok = __all_sync(0xffffffffu, ok);
             __syncwarp();
-            c.ver = ok ? ver : -1;
+            c.ver = ver;
             c.K = K;
-            if (!ok) {
-                cand = true;
+            double mg;
+            const int k_new = f_warp_pick(ew, K + 1, c.u, &mg);
+            if (k_new != k_old) {
+                cand = true;   // includes -2 (an untrusted / overflowed entry): the step redoes it in full
+                // a plain move between two live components needs no second evaluation if it turns out to be
+                // the first candidate: every datum in front of it stayed, so the records it saw are current
+                if (k_new >= 0 && k_new < K) { drawn = k_new; my_margin = fmin(my_margin, mg); }
             } else {
-                double mg;
-                const int k_new = f_warp_pick(ew, K + 1, c.u, &mg);
-                if (k_new != k_old) {
-                    cand = true;   // includes -2: the step redoes it in the log domain
-                    // a plain move between two live components needs no second evaluation if it turns out to be
-                    // the first candidate: every datum in front of it stayed, so the records it saw are current
-                    if (k_new >= 0 && k_new < K) { drawn = k_new; my_margin = fmin(my_margin, mg); }
-                } else {
-                    my_margin = fmin(my_margin, mg);
-                }
+                my_margin = fmin(my_margin, mg);
             }
             __syncwarp();
         }
@@ -1011,7 +1056,8 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
         sh.margin_bits = (unsigned long long)__double_as_longlong(one);
         sh.round = 0;
         sh.k_new = 0; sh.need_explicit = 0; sh.explicit_done = 0; sh.refresh_a = 0; sh.refresh_b = 0;
-        sh.ver = 1; sh.dirty_a = sh.dirty_b = -1; sh.dirty_all = 1;
+        sh.ver = 1; sh.dall_ver = 1;
+        for (int t = 0; t < DLOG; ++t) sh.dlog_a[t] = sh.dlog_b[t] = -1;
         for (int t = 0; t < PH_COUNT; ++t) sh.prof[t] = 0;
         sh.prof_last = clock64();
         sh.mode = (p.engine == 2) ? 1 : ((p.engine == 1) ? 0 : (p.init_gap >= GAP_TO_WIN ? 1 : 0));
@@ -1067,7 +1113,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
 
     WCache cache;
     cache.nj = (long long)blockIdx.x + (long long)gridDim.x * (tid >> 5);
-    cache.j = -1; cache.i = 0; cache.uid = -1; cache.ver = -1; cache.K = 0; cache.u = 0.0; cache.lp = 0.0;
+    cache.j = -1; cache.i = 0; cache.uid = -1; cache.stage = 0; cache.ver = -1; cache.K = 0; cache.u = 0.0; cache.lp = 0.0;
     int seq = 0;
     // minimum margin over this warp's window evaluations (committed and discarded alike: a lower bound of the
     // chain's true minimum margin); folded into the control block once, at the end
@@ -1090,7 +1136,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
                 sh.gap = 0.5 * sh.gap + 0.5 * (double)nb / ((double)mv + 0.5);
                 sh.seq_data += done;
                 sh.pos = pos + done;
-                sh.dirty_all = 1;   // several changes since the evaluators last looked
+                sh.dall_ver = sh.ver;   // several changes since the evaluators last looked
                 if (p.engine == 0 && sh.gap >= GAP_TO_WIN) sh.mode = 1;
                 sh.win = f_next_window(sh.gap, sh.pos, p.N);
             }
