@@ -24,6 +24,7 @@
 //     element), counters.  Replicas read mutable global state only between two grid barriers.
 #pragma once
 #include "bgmm_sweep.cuh"
+#include <assert.h>
 
 namespace bgmm {
 namespace fast {
@@ -104,7 +105,7 @@ static __device__ __noinline__ void f_grid_barrier(Ctl *c) {
         } else {
             const long long t0 = clock64();
             while (ld_acquire_u32(&c->bar_gen) == gen) {
-                if (clock64() - t0 > 8000000000LL) __trap();
+                if (clock64() - t0 > 8000000000LL) assert(false && "bgmm watchdog 1: replicas stopped agreeing");
             }
         }
         __threadfence();
@@ -147,7 +148,7 @@ static __device__ __noinline__ void f_round_barrier(Ctl *c, const unsigned long 
         } else {
             const long long t0 = clock64();
             while (ld_acquire_u32(&c->bar_gen) == gen) {
-                if (clock64() - t0 > 8000000000LL) __trap();
+                if (clock64() - t0 > 8000000000LL) assert(false && "bgmm watchdog 2: replicas stopped agreeing");
             }
         }
         __threadfence();
@@ -916,7 +917,7 @@ __device__ __forceinline__ bool f_row_usable(const FSh &sh, const WCache &c, int
 // ---------------------------------------------------------------------------------------------
 template <int DP>
 __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos, long long win, int K,
-                              unsigned long long *first_slot, WCache &c, double &my_margin) {
+                              unsigned long long *first_slot, unsigned int round, WCache &c, double &my_margin) {
     using Ly = Lay<DP>;
     constexpr int ST = Ly::KS;
     const FSh &sh = *s.sh;
@@ -994,7 +995,9 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
             __syncwarp();
         }
         if (cand) {
-            double *mv = p.mvbuf + (size_t)gw * (DP + MV_EXTRA);
+            // mover slots are double-buffered by round parity: a replica that lags (nothing bounds by how much) may
+            // still be fetching the previous round's winner from this warp's other slot; it cannot lag two rounds
+            double *mv = p.mvbuf + ((size_t)(round & 1u) * G * NWARP + gw) * (DP + MV_EXTRA);
             if (lane < DP) __stcg(mv + lane, xw[lane]);
             if (lane == 0) {
                 __stcg(mv + DP, c.u);
@@ -1100,7 +1103,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
         uint32_t okw = 0;
         const long long t0 = clock64();
         while (!okw) {
-            if (clock64() - t0 > 8000000000LL) __trap();
+            if (clock64() - t0 > 8000000000LL) assert(false && "bgmm watchdog 3: replicas stopped agreeing");
             asm volatile(
                 "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                 : "=r"(okw)
@@ -1147,7 +1150,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             const int K = sh.K;
             const long long win = sh.win;
             F_PROF(PH_HEAD);
-            f_window_eval<DP>(p, s, pos, win, K, slot, cache, win_margin);
+            f_window_eval<DP>(p, s, pos, win, K, slot, r, cache, win_margin);
             __syncthreads();
             F_PROF(PH_WINEVAL);
             f_round_barrier(ctl, slot, &sh.fv);
@@ -1158,7 +1161,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             const long long end = pos + win;
             if (f < end) {
                 // every CTA resolves the first candidate itself, from the inputs its evaluator published
-                const double *mv = p.mvbuf + (size_t)(fv & 4095ULL) * (DP + MV_EXTRA);
+                const double *mv = p.mvbuf + ((size_t)(r & 1u) * gridDim.x * NWARP + (size_t)(fv & 4095ULL)) * (DP + MV_EXTRA);
                 if (tid < DP + MV_EXTRA) {
                     const double v = __ldcg(mv + tid);
                     if (tid < DP) s.xb[tid] = v;
