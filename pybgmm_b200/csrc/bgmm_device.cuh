@@ -69,6 +69,7 @@ struct Ctl {
     double gap;         // running estimate of the number of data between two movers
     long long explicit_evals, refreshes;
     long long prof[16];            // phase clocks of CTA 0 (cycles), see bgmm_fast.cuh
+    unsigned long long wsum[8], wcnt[8], wmax[8];  // evaluator unit clocks by category (profile builds)
 };
 
 struct Params {

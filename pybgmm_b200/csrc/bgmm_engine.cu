@@ -532,6 +532,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     c.moves = c.births = c.deaths = c.evals = c.windows = c.seq_data = c.wasted = 0;
     c.explicit_evals = c.refreshes = 0;
     memset(c.prof, 0, sizeof(c.prof));
+    memset(c.wsum, 0, sizeof(c.wsum)); memset(c.wcnt, 0, sizeof(c.wcnt)); memset(c.wmax, 0, sizeof(c.wmax));
     const double one = 1.0;
     memcpy(&c.margin_bits, &one, 8);
     c.error = 0; c.bar_count = 0; c.pos = 0; c.win = 0; c.first = POS_INF; c.n_dirty = 0;
@@ -593,6 +594,13 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         out->device_ms = ms;
         out->explicit_evals = c.explicit_evals; out->refreshes = c.refreshes; out->generic_from = generic_from;
         for (int t = 0; t < 16; ++t) out->phase_cycles[t] = c.prof[t];
+        if (getenv("BGMM_WPROF")) {
+            static const char *nm[7] = {"idle", "load", "chunk", "fresh", "stay", "cand", "full"};
+            for (int t = 0; t < 7; ++t)
+                if (c.wcnt[t])
+                    fprintf(stderr, "  unit %-5s n=%10llu mean=%8.0f max=%8llu cycles\n", nm[t], c.wcnt[t],
+                            (double)c.wsum[t] / (double)c.wcnt[t], c.wmax[t]);
+        }
         out->launches = h->launches; out->sweep_kernel_ms = ms_k;
     }
     if (c.error == BGMM_EKMAX) return fail(BGMM_EKMAX, "a new component would exceed K_max (the reference raises IndexError)");

@@ -52,7 +52,23 @@ enum { PH_STAGE = 0, PH_HEAD, PH_EVAL, PH_DRAW, PH_UPDATE, PH_SCALARS, PH_WINEVA
         }                                                             \
     } while (0)
 #define F_COUNT(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) s.sh->prof[slot] += 1; } while (0)
+// evaluator unit categories: 0 idle, 1 load inputs, 2 evaluate a chunk, 3 keep a waiting row fresh, 4 decide: stay,
+// 5 decide: candidate, 6 decide after a full evaluation
+#define F_WCAT(cat) wcat_ = (cat)
+#define F_WPROF_BEGIN() int wcat_ = 0; const long long wt0_ = clock64()
+#define F_WPROF_END()                                                                         \
+    do {                                                                                      \
+        if ((threadIdx.x & 31) == 0) {                                                        \
+            const unsigned long long dt_ = (unsigned long long)(clock64() - wt0_);            \
+            atomicAdd(&p.ctl->wsum[wcat_], dt_);                                              \
+            atomicAdd(&p.ctl->wcnt[wcat_], 1ULL);                                             \
+            atomicMax(&p.ctl->wmax[wcat_], dt_);                                              \
+        }                                                                                     \
+    } while (0)
 #else
+#define F_WCAT(cat) do { } while (0)
+#define F_WPROF_BEGIN() do { } while (0)
+#define F_WPROF_END() do { } while (0)
 #define F_PROF(slot) do { } while (0)
 #define F_COUNT(slot) do { } while (0)
 #endif
@@ -904,6 +920,24 @@ __device__ __forceinline__ bool f_row_usable(const FSh &sh, const WCache &c, int
     return c.stage >= 2 && c.K <= K && c.ver >= sh.dall_ver && ver - c.ver <= DLOG - 1;
 }
 
+// bring a complete row evaluated at version c.ver up to the current version: re-evaluate the entries of the components
+// touched since (two per version, from the dirty log)
+template <int DP>
+__device__ __forceinline__ void f_row_update(const FSmem<DP> &s, WCache &c, int K, int ver, int k_old, double wref,
+                                             const double *xw, double *ew) {
+    using Ly = Lay<DP>;
+    const FSh &sh = *s.sh;
+    const int lane = threadIdx.x & 31;
+    const int nd = 2 * (ver - c.ver);
+    if (lane < nd) {
+        const int v = c.ver + 1 + (lane >> 1);
+        const int k = (lane & 1) ? sh.dlog_b[v & (DLOG - 1)] : sh.dlog_a[v & (DLOG - 1)];
+        if (k >= 0 && k < K) ew[k] = f_eval_lane<DP, Ly::KS>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0);
+    }
+    __syncwarp();
+    c.ver = ver;
+}
+
 // ---------------------------------------------------------------------------------------------
 // One round of a warp's evaluator duty.  The warp owns the scan positions congruent to its global id; `c` holds
 // the next one (c.nj) in some stage of preparation.
@@ -932,17 +966,24 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
     const int ver = sh.ver;
     const int nch = (K + 31) >> 5;
     if (c.j != c.nj) { c.j = c.nj; c.stage = 0; }
+    F_WPROF_BEGIN();
     if (c.j >= end) {
         // not needed this round: one unit of preparation
         if (c.j < p.N) {
             if (c.stage == 0) {
+                F_WCAT(1);
                 f_load_inputs<DP>(p, c, xw);
             } else if (c.j - pos < 3 * win) {
-                // evaluate just in time: a row prepared too early would outlive the dirty log
+                // evaluate just in time: a row prepared too early would outlive the dirty log.  (Keeping waiting rows
+                // current round by round was measured slower: every warp busy every round slows the critical one.)
                 if (c.stage >= 2 && !f_row_usable(sh, c, K, ver)) c.stage = 1;
-                if (c.stage - 1 < nch) f_eval_chunk<DP>(p, s, c, K, ver, xw, ew);
+                if (c.stage - 1 < nch) {
+                    F_WCAT(2);
+                    f_eval_chunk<DP>(p, s, c, K, ver, xw, ew);
+                }
             }
         }
+        F_WPROF_END();
         return;
     }
     bool first_pass = true;
@@ -968,16 +1009,9 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
             const double wref = p.log_alpha + c.lp;
             if (c.stage >= 2 && !f_row_usable(sh, c, K, ver)) c.stage = 1;
             const bool fresh = (c.stage == 1);
+            F_WCAT(fresh ? 6 : 4);
             while (c.stage - 1 < nch) f_eval_chunk<DP>(p, s, c, K, ver, xw, ew);
-            if (!fresh && c.ver != ver) {
-                // entries of the components touched since the row's version (two per version, from the dirty log)
-                const int nd = 2 * (ver - c.ver);
-                if (lane < nd) {
-                    const int v = c.ver + 1 + (lane >> 1);
-                    const int k = (lane & 1) ? sh.dlog_b[v & (DLOG - 1)] : sh.dlog_a[v & (DLOG - 1)];
-                    if (k >= 0 && k < K) ew[k] = f_eval_lane<DP, ST>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0);
-                }
-            }
+            if (!fresh && c.ver != ver) f_row_update<DP>(s, c, K, ver, k_old, wref, xw, ew);
             if (lane == 0) ew[K] = 1.0;
             __syncwarp();
             c.ver = ver;
@@ -995,6 +1029,7 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
             __syncwarp();
         }
         if (cand) {
+            F_WCAT(5);
             // mover slots are double-buffered by round parity: a replica that lags (nothing bounds by how much) may
             // still be fetching the previous round's winner from this warp's other slot; it cannot lag two rounds
             double *mv = p.mvbuf + ((size_t)(round & 1u) * G * NWARP + gw) * (DP + MV_EXTRA);
@@ -1012,6 +1047,7 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
             break;
         }
     }
+    F_WPROF_END();
 }
 
 // length of the next window: about twice the running gap between movers, whole rows of one datum per SM
