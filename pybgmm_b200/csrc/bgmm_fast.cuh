@@ -37,6 +37,9 @@ constexpr int NB_MAX = 6;             // weights per lane in the draw: supports 
 constexpr int E_NEED_GENERIC = 1;     // internal: a birth would exceed the resident capacity -> generic engine
 constexpr double GAP_TO_WIN = 6.0, GAP_TO_SEQ = 3.0;
 constexpr int WIN_PASSES_MAX = 8;
+constexpr int BULK_PASSES_MAX = 4;     // passes of the thread-per-datum evaluator in one window
+constexpr int BULK_MIN_ROWS = TF / 2;   // windows of at least this many data per SM use it: a pass of the
+                                        // thread-per-datum evaluator has a long fixed latency (K evaluations in series)
 constexpr int DLOG = 16;              // versions of the dirty log (power of two)
 constexpr int MV_EXTRA = 5;           // mover slot: x[DP], u, log prior, i, uid, drawn component (-1: full step)
 // phase clocks (CTA 0, thread 0; cycles): reported through bgmm_sweep_stats.phase_cycles
@@ -1050,10 +1053,105 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
     F_WPROF_END();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Long windows (movers far apart): a THREAD per datum, components in a loop, so every record element is one
+// broadcast shared-memory read for 32 data and the evaluation is FP64-issue bound instead of latency bound.
+// Only the stay test is needed here, and it needs no stored row: with e_k = exp(weight_k - wref) accumulated in
+// component order, total s, prefix P = sum_{k < k_old} e_k and e_own decide "stay" iff P <= u s < P + e_own
+// (utils.py:15-20).  Anything else is a candidate, published without inputs (low bits 4095): every CTA then stages
+// the datum from global memory and resolves it in full.
+// Scan position j is owned by CTA (j % grid), thread ((j / grid) % TF).
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned long long BULK_TAG = 4095ULL;
+
+template <int DP>
+__device__ __noinline__ void f_bulk_eval(const Params &p, const FSmem<DP> &s, long long pos, long long win, int K,
+                                         unsigned long long *first_slot, double &my_margin) {
+    using Ly = Lay<DP>;
+    constexpr int ST = Ly::KS;
+    const long long G = gridDim.x;
+    const long long end = pos + win;
+    const long long stride = G * TF;
+    long long j = pos + (long long)blockIdx.x + G * threadIdx.x;   // relative ownership: windows are long here
+    const double *rec = s.rec;
+    bool first_pass = true;
+    for (; j < end; j += stride) {
+        if (!first_pass) {
+            // later passes: stop once a candidate in front of this datum is known (it would be redone)
+            if ((long long)(__ldcg(first_slot) >> 12) < j) break;
+        }
+        first_pass = false;
+        const long long i = p.order ? p.order[j] : j;
+        const int uid = __ldcg(p.z_uid + i);
+        bool cand = (uid < 0);
+        int k_old = -1;
+        if (!cand) {
+            k_old = s.slot_of_uid[uid];
+            if (rec[(Ly::SC + F_N) * ST + k_old] == 1.0) cand = true;  // the component would die
+        }
+        if (!cand) {
+            double x[DP];
+            const double *xr = p.X + (size_t)i * DP;
+            if (DP >= 2) {
+#pragma unroll
+                for (int a = 0; a < DP; a += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(xr + a);
+                    x[a] = v.x; x[a + 1] = v.y;
+                }
+            } else {
+                x[0] = xr[0];
+            }
+            const double wref = p.log_alpha + p.log_prior[i];
+            const double u = p.u[j];
+            double ssum = 0.0, pre = 0.0, eown = 0.0;
+            bool ok = true;
+#pragma unroll 1
+            for (int k = 0; k < K; ++k) {
+                const double *col = rec + k;   // uniform over the warp: broadcast reads
+                double q = 0.0;
+#pragma unroll
+                for (int a = 0; a < DP; ++a) {
+                    double r = 0.0;
+#pragma unroll
+                    for (int b = 0; b < a; ++b)
+                        r = fma(col[(a * (a + 1) / 2 + b) * ST], col[(Ly::MU + b) * ST] - x[b], r);
+                    const double da = col[(Ly::MU + a) * ST] - x[a];
+                    r = fma(0.5 * col[(a * (a + 1) / 2 + a) * ST], da, r);
+                    q = fma(da, r, q);
+                }
+                q *= 2.0;
+                const double *sc = col + Ly::SC * ST;
+                const bool own = (k == k_old);
+                const double arg = own ? 1.0 - sc[F_BETA * ST] * q : 1.0 + sc[F_G * ST] * q;
+                if (own && !(arg > OM_MIN)) { ok = false; break; }
+                const double hh = own ? 1.0 - sc[F_H * ST] : sc[F_H * ST];
+                const double cc = own ? sc[F_CWO * ST] : sc[F_CW * ST];
+                const double t = (cc - hh * log(arg)) - wref;
+                const double e = (t < EXP_CUTOFF) ? 0.0 : exp(t);
+                if (k < k_old) pre += e;
+                if (own) eown = e;
+                ssum += e;
+            }
+            ssum += 1.0;   // the new-table entry: exp(wref - wref)
+            const double t0 = u * ssum;
+            if (!ok || !(ssum < INFINITY) || !(t0 >= pre) || !(t0 < pre + eown)) {
+                cand = true;
+            } else {
+                const double mg = fmin(t0 - pre, pre + eown - t0);
+                my_margin = fmin(my_margin, (double)__fdividef((float)mg, (float)ssum));
+            }
+        }
+        if (cand) {
+            atomicMin(first_slot, ((unsigned long long)j << 12) | BULK_TAG);
+            break;
+        }
+    }
+}
+
 // length of the next window: about twice the running gap between movers, whole rows of one datum per SM
 __device__ __forceinline__ long long f_next_window(double gap, long long pos, long long N) {
     const long long G = gridDim.x;
-    const long long wcap = G * NWARP * WIN_PASSES_MAX;
+    const long long wcap = G * TF * BULK_PASSES_MAX;
     long long win = (long long)fmin(2.0 * gap, (double)wcap);
     win = ((win + G - 1) / G) * G;
     if (win < G) win = G;
@@ -1186,7 +1284,9 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             const int K = sh.K;
             const long long win = sh.win;
             F_PROF(PH_HEAD);
-            f_window_eval<DP>(p, s, pos, win, K, slot, r, cache, win_margin);
+            const bool bulk = (win >= (long long)gridDim.x * BULK_MIN_ROWS);
+            if (bulk) f_bulk_eval<DP>(p, s, pos, win, K, slot, win_margin);
+            else f_window_eval<DP>(p, s, pos, win, K, slot, r, cache, win_margin);
             __syncthreads();
             F_PROF(PH_WINEVAL);
             f_round_barrier(ctl, slot, &sh.fv);
@@ -1195,7 +1295,17 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             const unsigned long long fv = sh.fv;
             const long long f = (long long)(fv >> 12);
             const long long end = pos + win;
-            if (f < end) {
+            if (f < end && (fv & 4095ULL) == BULK_TAG) {
+                // candidate of the thread-per-datum evaluator: stage it from global memory and resolve it in full
+                if (tid == 0) { sh.evals += (f - pos) * (long long)K; sh.wasted += end - (f + 1); }
+                __syncthreads();
+                f_run<DP>(p, s, f, 1, seq);
+                __syncthreads();
+                if (tid == 0) {
+                    sh.pos = f + (sh.error ? 0 : 1);
+                    sh.gap = 0.7 * sh.gap + 0.3 * (double)(f - pos + 1);
+                }
+            } else if (f < end) {
                 // every CTA resolves the first candidate itself, from the inputs its evaluator published
                 const double *mv = p.mvbuf + ((size_t)(r & 1u) * gridDim.x * NWARP + (size_t)(fv & 4095ULL)) * (DP + MV_EXTRA);
                 if (tid < DP + MV_EXTRA) {
@@ -1241,6 +1351,8 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
 
     // ---- epilogue: CTA 0 publishes the chain state ----
     __syncthreads();
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) win_margin = fmin(win_margin, __shfl_xor_sync(0xffffffffu, win_margin, o));
     if ((tid & 31) == 0 && win_margin < 1.0)
         atomicMin(&ctl->margin_bits, (unsigned long long)__double_as_longlong(win_margin));
     if (cta0) {
