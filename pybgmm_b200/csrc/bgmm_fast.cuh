@@ -521,6 +521,7 @@ __device__ __noinline__ void f_rank_one_warp(const Params &p, const FSmem<DP> &s
     const double den = (sign < 0) ? 1.0 - beta * sq : 1.0 + beta * sq;
     const double gam = (sign < 0) ? beta / den : -beta / den;
     const double rk2 = nt[NT_W + NT_RK];   // 1 / kappa(n2)
+    const double lg_den = log(den);        // every lane: overlaps the matrix update below instead of trailing it
 #pragma unroll 1
     for (int e = lane; e < Ly::PP; e += 32) {
         const int a = s.rc[e] >> 8, b = s.rc[e] & 0xff;
@@ -533,7 +534,7 @@ __device__ __noinline__ void f_rank_one_warp(const Params &p, const FSmem<DP> &s
     }
     if (lane == 0) {
         const double cnt = sc[F_CNT * ST] + 1.0;
-        f_write_scalars(sc, ST, n2, sc[F_LDS * ST] + log(den), cnt, nt, nt + NT_W);
+        f_write_scalars(sc, ST, n2, sc[F_LDS * ST] + lg_den, cnt, nt, nt + NT_W);
         FSh &sh = *s.sh;
         if (cnt >= (double)REFRESH_EVERY) { if (which == 0) sh.refresh_a = seq; else sh.refresh_b = seq; }
         if (which == 1) sh.moves += 1;
@@ -1073,7 +1074,11 @@ __device__ __noinline__ void f_bulk_eval(const Params &p, const FSmem<DP> &s, lo
     const long long end = pos + win;
     const long long stride = G * TF;
     long long j = pos + (long long)blockIdx.x + G * threadIdx.x;   // relative ownership: windows are long here
-    const double *rec = s.rec;
+    // the records start the kernel's dynamic shared array: addressing them through it (not through the generic
+    // pointer s.rec) makes the loads below LDS broadcasts instead of generic loads that queue in the LSU's
+    // local/global path (stall_lg_throttle in the converged-sweep profile)
+    extern __shared__ __align__(16) double smem_raw[];
+    const double *rec = smem_raw;
     bool first_pass = true;
     for (; j < end; j += stride) {
         if (!first_pass) {
@@ -1150,13 +1155,14 @@ __device__ __noinline__ void f_bulk_eval(const Params &p, const FSmem<DP> &s, lo
 
 // length of the next window: about twice the running gap between movers, whole rows of one datum per SM
 __device__ __forceinline__ long long f_next_window(double gap, long long pos, long long N) {
-    const long long G = gridDim.x;
-    const long long wcap = G * TF * BULK_PASSES_MAX;
-    long long win = (long long)fmin(2.0 * gap, (double)wcap);
+    // 32-bit / single precision on purpose: this runs on one thread between two rounds
+    const int G = (int)gridDim.x;
+    const int wcap = G * TF * BULK_PASSES_MAX;
+    int win = (int)fminf(2.0f * (float)gap, (float)wcap);
     win = ((win + G - 1) / G) * G;
     if (win < G) win = G;
-    if (win > N - pos) win = N - pos;
-    return win;
+    const long long left = N - pos;
+    return left < (long long)win ? left : (long long)win;
 }
 
 // ---------------------------------------------------------------------------------------------

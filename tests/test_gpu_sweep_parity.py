@@ -205,3 +205,21 @@ def test_long_chain_drift_control(gpu_lib):
         np.testing.assert_array_equal(ch.assignments(), orc.assignments)
     assert refreshes > 0
     _assert_state_equal(orc, ch)
+
+
+@pytest.mark.parametrize("D,cov", [(32, "full"), (64, "full"), (64, "diag"), (24, "full")])
+def test_high_dimensional_sweeps_match_oracle(gpu_lib, D, cov):
+    """D > 16 (BASELINE.json configs[3] is D = 64) runs on the generic engine: same exact parity bar."""
+    N, K_true, sweeps = 500, 4, 3
+    X, orc, ch = _pair(gpu_lib, N, D, K_true, cov, K_init=K_true)
+    rng = np.random.RandomState(21)
+    for s in range(sweeps):
+        u = rng.random_sample(N)
+        so = orc.sweep(u, 1.0)
+        sg = ch.sweep(1.0, 1.0, None, u)
+        assert (sg.K, sg.moves, sg.births, sg.deaths, sg.evals) == (so.K_end, so.moves, so.births, so.deaths, so.evals), s
+        np.testing.assert_array_equal(ch.assignments(), orc.assignments)
+    _assert_state_equal(orc, ch, check_inv=False)
+    idx = np.arange(0, N, 11)
+    np.testing.assert_allclose(ch.log_post_pred(idx), np.stack([orc.log_post_pred(i) for i in idx]), rtol=RTOL)
+    np.testing.assert_allclose(ch.log_marg(1.0), orc.log_marg(1.0), rtol=RTOL)
