@@ -80,28 +80,37 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary over the samples taken in [t0, t1] (the timed region); the sampler itself runs from the start of
+        the warm-up sweeps so that a short timed region still sees the clocks the device was running at under load."""
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def summarise(rows):
+            sm, mx, reasons = [], [], set()
+            for r in rows:
+                try:
+                    sm.append(float(r[2])); mx.append(float(r[3]))
+                except Exception:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[6:10]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        timed = [r for r in self.rows if t0 is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+        sm_t, mx_t, re_t = summarise(timed)
+        sm_a, mx_a, re_a = summarise(self.rows)
+        sm, mx = (sm_t, mx_t) if sm_t else (sm_a, mx_a)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(re_t | re_a), "samples": len(sm_t), "samples_incl_warmup_under_load": len(sm_a)}
 
 
 def measured_peak():
@@ -353,22 +362,23 @@ def run_ours(a):
     d_o = [torch.from_numpy(o).to(dev) if o is not None else None for o in orders]
     d_u = [torch.from_numpy(u).to(dev) for u in unis]
     chain.set_assignments(z0)
+    sampler_thread = ClockSampler(local_rank)
+    if rank == 0:
+        sampler_thread.start()
     warm = []
     for s in range(W):
         warm.append(chain.sweep_dev(1.0, pw(s), 0 if d_o[s] is None else d_o[s].data_ptr(), d_u[s].data_ptr()))
     sync_all()
-    sampler_thread = ClockSampler(local_rank)
-    if rank == 0:
-        sampler_thread.start()
-        time.sleep(0.25)
     sync_all()
+    t_region0 = time.time()
     e0.record(stream)
     stats = []
     for s in range(W, W + K):
         stats.append(chain.sweep_dev(1.0, pw(s), 0 if d_o[s] is None else d_o[s].data_ptr(), d_u[s].data_ptr()))
     e1.record(stream)
     sync_all()
-    clocks = sampler_thread.stop() if rank == 0 else None
+    t_region1 = time.time()
+    clocks = sampler_thread.stop(t_region0, t_region1) if rank == 0 else None
     ms = reduce_max(e0.elapsed_time(e1))
     evals = float(sum(st.evals for st in stats))
     total_evals = reduce_sum(evals)
