@@ -109,6 +109,7 @@ struct Params {
     double *recB;
     double *recB_prior;
     double *mvbuf;            // per evaluator warp: the inputs of the candidate it published
+    const double *fmtab;      // log / exp tables of bgmm_fastmath.cuh
     double *ntab;             // count table: 8 doubles per count n = 0..N (bgmm_fast.cuh NT_*)
     int KS, Kcap;
 };

@@ -205,7 +205,7 @@ static void free_all(bgmm_handle *h) {
     cudaFree(h->d_S0); cudaFree(h->d_z); cudaFree(h->d_slot_of_uid); cudaFree(h->d_uid_of_slot); cudaFree(h->d_uid_free);
     cudaFree(h->d_counts); cudaFree(h->d_num); cudaFree(h->d_S); cudaFree(h->d_rec); cudaFree(h->d_wbuf);
     cudaFree(h->d_rec_prior); cudaFree(h->d_ctl); cudaFree(h->d_err); cudaFree(h->d_u); cudaFree(h->d_order);
-    cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf); cudaFree(h->d_ntab);
+    cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf); cudaFree(h->d_ntab); cudaFree(h->d_fmtab);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
@@ -595,8 +595,8 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         out->explicit_evals = c.explicit_evals; out->refreshes = c.refreshes; out->generic_from = generic_from;
         for (int t = 0; t < 16; ++t) out->phase_cycles[t] = c.prof[t];
         if (getenv("BGMM_WPROF")) {
-            static const char *nm[7] = {"idle", "load", "chunk", "fresh", "stay", "cand", "full"};
-            for (int t = 0; t < 7; ++t)
+            static const char *nm[8] = {"idle", "load", "chunk", "rowup", "stay", "cand", "full", "pick"};
+            for (int t = 0; t < 8; ++t)
                 if (c.wcnt[t])
                     fprintf(stderr, "  unit %-5s n=%10llu mean=%8.0f max=%8llu cycles\n", nm[t], c.wcnt[t],
                             (double)c.wsum[t] / (double)c.wcnt[t], c.wmax[t]);

@@ -24,6 +24,7 @@
 //     element), counters.  Replicas read mutable global state only between two grid barriers.
 #pragma once
 #include "bgmm_sweep.cuh"
+#include "bgmm_fastmath.cuh"
 #include <assert.h>
 
 namespace bgmm {
@@ -59,6 +60,16 @@ enum { PH_STAGE = 0, PH_HEAD, PH_EVAL, PH_DRAW, PH_UPDATE, PH_SCALARS, PH_WINEVA
 // 5 decide: candidate, 6 decide after a full evaluation
 #define F_WCAT(cat) wcat_ = (cat)
 #define F_WPROF_BEGIN() int wcat_ = 0; const long long wt0_ = clock64()
+#define F_WSUB_BEGIN() const long long ws0_ = clock64()
+#define F_WSUB_END(cat)                                                                       \
+    do {                                                                                      \
+        if ((threadIdx.x & 31) == 0) {                                                        \
+            const unsigned long long dt_ = (unsigned long long)(clock64() - ws0_);            \
+            atomicAdd(&p.ctl->wsum[cat], dt_);                                                \
+            atomicAdd(&p.ctl->wcnt[cat], 1ULL);                                               \
+            atomicMax(&p.ctl->wmax[cat], dt_);                                                \
+        }                                                                                     \
+    } while (0)
 #define F_WPROF_END()                                                                         \
     do {                                                                                      \
         if ((threadIdx.x & 31) == 0) {                                                        \
@@ -72,6 +83,8 @@ enum { PH_STAGE = 0, PH_HEAD, PH_EVAL, PH_DRAW, PH_UPDATE, PH_SCALARS, PH_WINEVA
 #define F_WCAT(cat) do { } while (0)
 #define F_WPROF_BEGIN() do { } while (0)
 #define F_WPROF_END() do { } while (0)
+#define F_WSUB_BEGIN() do { } while (0)
+#define F_WSUB_END(cat) do { } while (0)
 #define F_PROF(slot) do { } while (0)
 #define F_COUNT(slot) do { } while (0)
 #endif
@@ -290,7 +303,7 @@ __device__ __forceinline__ void f_write_scalars(double *sc, int st, double n, do
 // ---------------------------------------------------------------------------------------------
 template <int DP, int ST>
 __device__ __noinline__ double f_eval_lane(const double *__restrict__ col, const double *__restrict__ x, int own,
-                                           double wref, int want_log) {
+                                           double wref, int want_log, const double *__restrict__ fmtab) {
     using Ly = Lay<DP>;
     // note: operands stay generic pointers on purpose.  Passing shared-window offsets (true LDS) was measured 15-40%
     // slower: the compiler then schedules each load right before its use instead of hoisting the batch.
@@ -319,9 +332,9 @@ __device__ __noinline__ double f_eval_lane(const double *__restrict__ col, const
         hh = sc[F_H * ST];
         cc = sc[F_CW * ST];
     }
-    const double t = (cc - hh * log(arg)) - wref;
+    const double t = (cc - hh * fm::f_log(arg, fmtab)) - wref;
     if (want_log) return t;
-    return (t < EXP_CUTOFF) ? 0.0 : exp(t);
+    return (t < EXP_CUTOFF) ? 0.0 : fm::f_exp(t, fmtab);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -622,7 +635,7 @@ __device__ __noinline__ void f_explicit_own(const Params &p, const FSmem<DP> &s,
             if (!okf) {
                 sh.error = -4;
             } else {
-                ew[k_old] = f_eval_lane<DP, 1>(s.tmprec, xs, 0, wref, 0);
+                ew[k_old] = f_eval_lane<DP, 1>(s.tmprec, xs, 0, wref, 0, p.fmtab);
                 sh.explicit_done = seq;
                 sh.explicit_evals += 1;
             }
@@ -639,8 +652,8 @@ __device__ __noinline__ void f_log_domain_draw(const Params &p, const FSmem<DP> 
     FSh &sh = *s.sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < K) {
-        if (expl && tid == k_old) ew[tid] = f_eval_lane<DP, 1>(s.tmprec, xs, 0, wref, 1);
-        else ew[tid] = f_eval_lane<DP, Ly::KS>(s.rec + tid, xs, (own_live && tid == k_old) ? 1 : 0, wref, 1);
+        if (expl && tid == k_old) ew[tid] = f_eval_lane<DP, 1>(s.tmprec, xs, 0, wref, 1, p.fmtab);
+        else ew[tid] = f_eval_lane<DP, Ly::KS>(s.rec + tid, xs, (own_live && tid == k_old) ? 1 : 0, wref, 1, p.fmtab);
     } else if (tid == K) {
         ew[K] = 0.0;
     }
@@ -797,7 +810,7 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
 
     // phase A: exp(weight - wref) of every live component (crpmm.py:68-75), thread k evaluates component k
     if (tid < K) {
-        const double e = f_eval_lane<DP, ST>(s.rec + tid, xs, (own_live && tid == k_old) ? 1 : 0, wref, 0);
+        const double e = f_eval_lane<DP, ST>(s.rec + tid, xs, (own_live && tid == k_old) ? 1 : 0, wref, 0, p.fmtab);
         if (e != e) sh.need_explicit = seq;
         ew[tid] = e;
     } else if (tid == K) {
@@ -913,7 +926,7 @@ __device__ __forceinline__ void f_eval_chunk(const Params &p, const FSmem<DP> &s
     const int k = chunk * 32 + lane;
     if (k < K) {
         const int k_old = (c.uid >= 0) ? s.slot_of_uid[c.uid] : -1;
-        ew[k] = f_eval_lane<DP, Ly::KS>(s.rec + k, xw, k == k_old ? 1 : 0, p.log_alpha + c.lp, 0);
+        ew[k] = f_eval_lane<DP, Ly::KS>(s.rec + k, xw, k == k_old ? 1 : 0, p.log_alpha + c.lp, 0, p.fmtab);
     }
     __syncwarp();
     c.stage += 1;
@@ -927,8 +940,8 @@ __device__ __forceinline__ bool f_row_usable(const FSh &sh, const WCache &c, int
 // bring a complete row evaluated at version c.ver up to the current version: re-evaluate the entries of the components
 // touched since (two per version, from the dirty log)
 template <int DP>
-__device__ __forceinline__ void f_row_update(const FSmem<DP> &s, WCache &c, int K, int ver, int k_old, double wref,
-                                             const double *xw, double *ew) {
+__device__ __forceinline__ void f_row_update(const Params &p, const FSmem<DP> &s, WCache &c, int K, int ver, int k_old,
+                                             double wref, const double *xw, double *ew) {
     using Ly = Lay<DP>;
     const FSh &sh = *s.sh;
     const int lane = threadIdx.x & 31;
@@ -936,7 +949,7 @@ __device__ __forceinline__ void f_row_update(const FSmem<DP> &s, WCache &c, int 
     if (lane < nd) {
         const int v = c.ver + 1 + (lane >> 1);
         const int k = (lane & 1) ? sh.dlog_b[v & (DLOG - 1)] : sh.dlog_a[v & (DLOG - 1)];
-        if (k >= 0 && k < K) ew[k] = f_eval_lane<DP, Ly::KS>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0);
+        if (k >= 0 && k < K) ew[k] = f_eval_lane<DP, Ly::KS>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0, p.fmtab);
     }
     __syncwarp();
     c.ver = ver;
@@ -1015,13 +1028,22 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
             const bool fresh = (c.stage == 1);
             F_WCAT(fresh ? 6 : 4);
             while (c.stage - 1 < nch) f_eval_chunk<DP>(p, s, c, K, ver, xw, ew);
-            if (!fresh && c.ver != ver) f_row_update<DP>(s, c, K, ver, k_old, wref, xw, ew);
+            if (!fresh && c.ver != ver) {
+                F_WSUB_BEGIN();
+                f_row_update<DP>(p, s, c, K, ver, k_old, wref, xw, ew);
+                F_WSUB_END(3);
+            }
             if (lane == 0) ew[K] = 1.0;
             __syncwarp();
             c.ver = ver;
             c.K = K;
             double mg;
-            const int k_new = f_warp_pick(ew, K + 1, c.u, &mg);
+            int k_new;
+            {
+                F_WSUB_BEGIN();
+                k_new = f_warp_pick(ew, K + 1, c.u, &mg);
+                F_WSUB_END(7);
+            }
             if (k_new != k_old) {
                 cand = true;   // includes -2 (an untrusted / overflowed entry): the step redoes it in full
                 // a plain move between two live components needs no second evaluation if it turns out to be
@@ -1079,6 +1101,7 @@ __device__ __noinline__ void f_bulk_eval(const Params &p, const FSmem<DP> &s, lo
     // local/global path (stall_lg_throttle in the converged-sweep profile)
     extern __shared__ __align__(16) double smem_raw[];
     const double *rec = smem_raw;
+    const double *fmtab = p.fmtab;
     bool first_pass = true;
     for (; j < end; j += stride) {
         if (!first_pass) {
@@ -1131,8 +1154,8 @@ __device__ __noinline__ void f_bulk_eval(const Params &p, const FSmem<DP> &s, lo
                 if (own && !(arg > OM_MIN)) { ok = false; break; }
                 const double hh = own ? 1.0 - sc[F_H * ST] : sc[F_H * ST];
                 const double cc = own ? sc[F_CWO * ST] : sc[F_CW * ST];
-                const double t = (cc - hh * log(arg)) - wref;
-                const double e = (t < EXP_CUTOFF) ? 0.0 : exp(t);
+                const double t = (cc - hh * fm::f_log(arg, fmtab)) - wref;
+                const double e = (t < EXP_CUTOFF) ? 0.0 : fm::f_exp(t, fmtab);
                 if (k < k_old) pre += e;
                 if (own) eown = e;
                 ssum += e;
