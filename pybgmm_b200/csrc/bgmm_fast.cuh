@@ -338,6 +338,55 @@ __device__ __noinline__ double f_eval_lane(const double *__restrict__ col, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same quantity for TWO components at once, rows of B over the 16 lanes of each half-warp (half 0: component
+// ka, half 1: kb; -1 = none): the latency-critical form used to bring a cached row up to date after ONE move --
+// 16-term dot products and a 4-step shuffle reduction instead of a 136-term chain per lane.  Same formula as
+// f_eval_lane, different summation order (agreement to rounding, ~1e-16).  Whole warp must call.
+// ---------------------------------------------------------------------------------------------
+template <int DP>
+__device__ __noinline__ void f_eval_rows2(const double *__restrict__ rec, const double *__restrict__ x, int ka, int kb,
+                                          int k_old, double wref, double *__restrict__ ew,
+                                          const double *__restrict__ fmtab) {
+    using Ly = Lay<DP>;
+    constexpr int ST = Ly::KS;
+    const int lane = threadIdx.x & 31;
+    const int r = lane & 15, half = lane >> 4;
+    const int k = half ? kb : ka;
+    const bool act = (k >= 0) && (r < DP);
+    const double *col = rec + (k >= 0 ? k : 0);
+    const double dr = act ? col[(Ly::MU + r) * ST] - x[r] : 0.0;
+    const double *row = col + (size_t)(r * (r + 1) / 2) * ST;   // element (r, 0)
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int b = 0; b < DP; b += 2) {
+        const double d0 = __shfl_sync(0xffffffffu, dr, (half << 4) + b, 32);
+        const double d1 = __shfl_sync(0xffffffffu, dr, (half << 4) + ((b + 1) & 15), 32);
+        if (act && b < r) a0 = fma(row[(size_t)b * ST], d0, a0);
+        if (act && b + 1 < r) a1 = fma(row[(size_t)(b + 1) * ST], d1, a1);
+    }
+    double t = act ? dr * fma(0.5 * row[(size_t)r * ST], dr, a0 + a1) : 0.0;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (r == 0 && k >= 0) {
+        const double q = 2.0 * t;
+        const double *sc = col + Ly::SC * ST;
+        const bool own = (k == k_old);
+        const double arg = own ? 1.0 - sc[F_BETA * ST] * q : 1.0 + sc[F_G * ST] * q;
+        double e;
+        if (own && !(arg > OM_MIN)) {
+            e = NAN;
+        } else {
+            const double hh = own ? 1.0 - sc[F_H * ST] : sc[F_H * ST];
+            const double cc = own ? sc[F_CWO * ST] : sc[F_CW * ST];
+            const double tt = (cc - hh * fm::f_log(arg, fmtab)) - wref;
+            e = (tt < EXP_CUTOFF) ? 0.0 : fm::f_exp(tt, fmtab);
+        }
+        ew[k] = e;
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // draw (utils.py:7-20) by one warp from the n = K + 1 unnormalised probabilities e[] in shared memory: the first
 // index whose inclusive cumulative sum exceeds u * total, else the last index.  Lane l owns the nb consecutive
 // entries starting at l * nb.  Returns the index, or -2 when the total is not finite / positive (the caller falls
@@ -946,6 +995,16 @@ __device__ __forceinline__ void f_row_update(const Params &p, const FSmem<DP> &s
     const FSh &sh = *s.sh;
     const int lane = threadIdx.x & 31;
     const int nd = 2 * (ver - c.ver);
+    if (nd == 2) {
+        // the common case on the critical path (a row re-examined right after one move): both components at once,
+        // rows over half-warps
+        int ka = sh.dlog_a[ver & (DLOG - 1)], kb = sh.dlog_b[ver & (DLOG - 1)];
+        if (ka >= K) ka = -1;
+        if (kb >= K) kb = -1;
+        f_eval_rows2<DP>(s.rec, xw, ka, kb, k_old, wref, ew, p.fmtab);
+        c.ver = ver;
+        return;
+    }
     if (lane < nd) {
         const int v = c.ver + 1 + (lane >> 1);
         const int k = (lane & 1) ? sh.dlog_b[v & (DLOG - 1)] : sh.dlog_a[v & (DLOG - 1)];
@@ -1067,8 +1126,8 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
                 __stcg(mv + DP + 3, __longlong_as_double((long long)uid));
                 __stcg(mv + DP + 4, __longlong_as_double((long long)drawn));
             }
-            __threadfence();
-            __syncwarp();
+            // no fence here: the slot is read only after the round's grid barrier, whose release (a __threadfence by
+            // this CTA's thread 0 after __syncthreads) already orders these stores before the barrier arrival
             if (lane == 0) atomicMin(first_slot, ((unsigned long long)j << 12) | gw);
             break;
         }
