@@ -52,6 +52,10 @@ struct Ctl {
     unsigned int pad_a[31];
     unsigned int bar_gen;
     unsigned int pad_b[31];
+    unsigned int rb_count;             // round barrier of the fast engine: arrivals ...
+    unsigned int pad_c[31];
+    unsigned long long rb_word;        // ... and (round tag << 44 | first candidate), released by the last arriver
+    unsigned long long pad_d[15];
     unsigned long long first3[3][16];  // per-round atomicMin targets of the fast engine (round r uses [r % 3][0])
     int K;
     int error;          // 0, or a BGMM_E* code

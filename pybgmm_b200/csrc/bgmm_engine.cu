@@ -535,7 +535,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     memset(c.wsum, 0, sizeof(c.wsum)); memset(c.wcnt, 0, sizeof(c.wcnt)); memset(c.wmax, 0, sizeof(c.wmax));
     const double one = 1.0;
     memcpy(&c.margin_bits, &one, 8);
-    c.error = 0; c.bar_count = 0; c.pos = 0; c.win = 0; c.first = POS_INF; c.n_dirty = 0;
+    c.error = 0; c.bar_count = 0; c.rb_count = 0; c.rb_word = 0; c.pos = 0; c.win = 0; c.first = POS_INF; c.n_dirty = 0;
     c.first3[0][0] = c.first3[1][0] = c.first3[2][0] = (unsigned long long)POS_INF;
     CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
     Params p = make_params(h);

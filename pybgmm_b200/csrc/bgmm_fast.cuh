@@ -165,26 +165,47 @@ struct FSh {
     long long prof[PH_COUNT], prof_last;
 };
 
-// the per-round barrier: as f_grid_barrier, and thread 0 reads the round's first-candidate word once for the CTA
-// (one request per CTA instead of one per warp on a single L2 line)
-static __device__ __noinline__ void f_round_barrier(Ctl *c, const unsigned long long *slot, unsigned long long *fv_out) {
+// The per-round barrier.  Arrival is one acq_rel atomic (its release orders this CTA's candidate publication, made
+// visible to thread 0 by the __syncthreads before it); the last CTA to arrive reads the round's candidate word --
+// every atomicMin on it happened before some arrival it has now acquired -- and releases
+//     (round tag << 44) | candidate word
+// in ONE 64-bit word, so a waiting CTA learns "everyone arrived" and "who is first" from the same load.  Critical
+// path: atomic (1 L2 trip) + slot read by the last arriver (1) + visibility of the word (1); no standalone fences.
+// `tag` is the index of this barrier within the sweep + 1 (20 bits, consecutive tags always differ).
+__device__ __forceinline__ unsigned int atom_add_acq_rel_u32(unsigned int *p, unsigned int v) {
+    unsigned int r;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+    return r;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+static __device__ __noinline__ void f_round_barrier(Ctl *c, const unsigned long long *slot, unsigned int tag,
+                                                    unsigned long long *fv_out) {
+    constexpr unsigned long long M44 = (1ULL << 44) - 1;
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int gen = ld_acquire_u32(&c->bar_gen);
-        __threadfence();
-        unsigned int prev = atomicAdd(&c->bar_count, 1u);
+        const unsigned long long want = (unsigned long long)(tag & 0xfffffu);
+        const unsigned int prev = atom_add_acq_rel_u32(&c->rb_count, 1u);
+        unsigned long long res;
         if (prev == gridDim.x - 1) {
-            c->bar_count = 0;
-            __threadfence();
-            st_release_u32(&c->bar_gen, gen + 1);
+            res = __ldcg(slot) & M44;
+            c->rb_count = 0;
+            st_release_u64(&c->rb_word, (want << 44) | res);
         } else {
             const long long t0 = clock64();
-            while (ld_acquire_u32(&c->bar_gen) == gen) {
-                if (clock64() - t0 > 8000000000LL) assert(false && "bgmm watchdog 2: replicas stopped agreeing");
+            unsigned long long w;
+            while (((w = ld_acquire_u64(&c->rb_word)) >> 44) != want) {
+                if (clock64() - t0 > 8000000000LL) assert(false && "bgmm watchdog 4: replicas stopped agreeing");
             }
+            res = w & M44;
         }
-        __threadfence();
-        *fv_out = __ldcg(slot);
+        *fv_out = res;
     }
     __syncthreads();
 }
@@ -1377,7 +1398,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             else f_window_eval<DP>(p, s, pos, win, K, slot, r, cache, win_margin);
             __syncthreads();
             F_PROF(PH_WINEVAL);
-            f_round_barrier(ctl, slot, &sh.fv);
+            f_round_barrier(ctl, slot, r + 1u, &sh.fv);
             F_PROF(PH_BARRIER);
             F_COUNT(PH_ROUNDS);
             const unsigned long long fv = sh.fv;
