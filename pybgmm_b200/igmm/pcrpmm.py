@@ -1,6 +1,13 @@
-"""Powered-CRP mixture model (mirror of pybgmm/igmm/pcrpmm.py:20-192)."""
+"""Powered-CRP mixture model on the GPU engine.
+
+API of `pybgmm/igmm/pcrpmm.py:20-192`.  What differs from CRPMM is decided on the host, per sweep, exactly as the
+reference decides it:
+  * the scan order is a fresh `np.random.permutation(N)` at the top of every sweep while the power is enabled
+    (`flag_power and n_power > 1`, pcrpmm.py:86-91) -- drawn from the global NumPy stream, like the reference;
+  * the count prior is log(n_k ** n_power) once `i_iter > power_burnin` (strictly; pcrpmm.py:105-112), log(n_k) before;
+  * the new-table weight stays log(alpha) (pcrpmm.py:116).
+"""
 import logging
-import time
 
 import numpy as np
 
@@ -11,32 +18,19 @@ logger = logging.getLogger(__name__)
 
 class PCRPMM(IGMM):
 
-    def __init__(self, X, kernel_prior, alpha, save_path, assignments="rand", K=1, K_max=None,
-                 covariance_type="full", device=0):
-        super(PCRPMM, self).__init__(X, kernel_prior, alpha, save_path, assignments=assignments, K=K, K_max=K_max,
-                                     covariance_type=covariance_type, device=device)
-
     def collapsed_gibbs_sampler(self, n_iter, true_assignments, n_power=1.01, power_burnin=0, num_saved=3,
                                 weight_first=True, flag_power=True, rng="reference"):
-        """`n_iter` sweeps of the pCRP sampler (pcrpmm.py:29-192): random scan order drawn from np.random at the top
-        of each sweep when the power is on (:86-91), count prior log(n_k ** n_power) once i_iter > power_burnin
-        (:105-112, strict), the new-table weight stays log(alpha) (:116)."""
-        record_dict = self.setup_record_dict()
-        start_time = time.time()
-        distribution_dict = self.setup_distribution_dict(num_saved)
-        for i_iter in range(n_iter):
-            if num_saved == self.components.K and i_iter > 1:
-                distribution_dict = self.update_distribution_dict(distribution_dict, weight_first)
-            if flag_power and n_power > 1:
+        powered_scan = bool(flag_power) and n_power > 1
+
+        def schedule(i_iter, n_points):
+            order = None
+            if powered_scan:
                 if i_iter % 20 == 0:
-                    logger.info(" Permutate data; " + "Power value: {}".format(n_power))
-                order = np.random.permutation(self.components.N)
-            else:
-                order = None
-            power = n_power if (flag_power and i_iter > power_burnin) else 1.0
-            self._device_sweep(power=power, order=order, rng=rng)
-            record_dict = self.update_record_dict(record_dict, i_iter, true_assignments, start_time)
-            start_time = time.time()
-        return record_dict, distribution_dict
+                    logger.info("sweep %d: random scan order, power %s", i_iter, n_power)
+                order = np.random.permutation(n_points)
+            use_power = bool(flag_power) and i_iter > power_burnin
+            return order, (n_power if use_power else 1.0)
+
+        return self._run_sweeps(n_iter, true_assignments, num_saved, weight_first, schedule, rng)
 
     gibbs_sample = collapsed_gibbs_sampler
