@@ -286,8 +286,17 @@ def run_ours(a):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    saved_stdout = None
     if world > 1:
+        # stdout carries the ONE JSON line: anything the collectives library prints there at communicator set-up (NCCL's
+        # version banner) goes to stderr instead -- file descriptor 1 is pointed at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is VERSION/INFO; stdout carries the JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if not torch.cuda.is_available() or _lib.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
@@ -444,6 +453,9 @@ def run_ours(a):
         line["gather_assignments_ms"] = gather_ms
     if world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(wl)
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
