@@ -1370,7 +1370,6 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
         const long long pos = sh.pos;
         if (pos >= p.N || sh.error != 0) break;
         const int mode = sh.mode;
-        __syncthreads();
         if (mode == 0) {
             const int nb = (int)min((long long)SEQ_BATCH, p.N - pos);
             const long long moves0 = sh.moves;
@@ -1396,7 +1395,9 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             const bool bulk = (win >= (long long)gridDim.x * BULK_MIN_ROWS);
             if (bulk) f_bulk_eval<DP>(p, s, pos, win, K, slot, win_margin);
             else f_window_eval<DP>(p, s, pos, win, K, slot, r, cache, win_margin);
-            __syncthreads();
+#ifdef BGMM_PROFILE
+            __syncthreads();   // only to attribute the waiting to the right phase clock
+#endif
             F_PROF(PH_WINEVAL);
             f_round_barrier(ctl, slot, r + 1u, &sh.fv);
             F_PROF(PH_BARRIER);
@@ -1437,8 +1438,8 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
                     f_move_phase<DP>(p, s, 0, s.slot_of_uid[s.uidb[0]], drawn, true, false, false, false, seq);
                 } else {
                     f_step<DP>(p, s, 0, seq);
+                    __syncthreads();   // f_step can return without a trailing barrier (stay / error paths)
                 }
-                __syncthreads();
                 if (tid == 0) {
                     sh.pos = f + (sh.error ? 0 : 1);
                     sh.gap = 0.7 * sh.gap + 0.3 * (double)(f - pos + 1);
