@@ -116,6 +116,7 @@ struct Params {
     const double *fmtab;      // log / exp tables of bgmm_fastmath.cuh
     double *ntab;             // count table: 8 doubles per count n = 0..N (bgmm_fast.cuh NT_*)
     int KS, Kcap;
+    float win_factor;         // window length = win_factor x running gap between movers
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -36,7 +36,8 @@ constexpr int SEQ_BATCH = 16;         // data staged per sequential batch
 constexpr int REFRESH_EVERY = 1024;   // rank-one updates of a record before it is rebuilt from the statistics
 constexpr int NB_MAX = 6;             // weights per lane in the draw: supports K + 1 <= 192
 constexpr int E_NEED_GENERIC = 1;     // internal: a birth would exceed the resident capacity -> generic engine
-constexpr double GAP_TO_WIN = 6.0, GAP_TO_SEQ = 3.0;
+// a window round costs about as much as two sequential steps, so windows pay from a gap of ~2 data between movers
+constexpr double GAP_TO_WIN = 2.5, GAP_TO_SEQ = 1.7;
 constexpr int WIN_PASSES_MAX = 8;
 constexpr int BULK_PASSES_MAX = 4;     // passes of the thread-per-datum evaluator in one window
 constexpr int BULK_MIN_ROWS = TF / 2;   // windows of at least this many data per SM use it: a pass of the
@@ -1257,11 +1258,11 @@ __device__ __noinline__ void f_bulk_eval(const Params &p, const FSmem<DP> &s, lo
 }
 
 // length of the next window: about twice the running gap between movers, whole rows of one datum per SM
-__device__ __forceinline__ long long f_next_window(double gap, long long pos, long long N) {
+__device__ __forceinline__ long long f_next_window(double gap, long long pos, long long N, float factor) {
     // 32-bit / single precision on purpose: this runs on one thread between two rounds
     const int G = (int)gridDim.x;
     const int wcap = G * TF * BULK_PASSES_MAX;
-    int win = (int)fminf(2.0f * (float)gap, (float)wcap);
+    int win = (int)fminf(factor * (float)gap, (float)wcap);
     win = ((win + G - 1) / G) * G;
     if (win < G) win = G;
     const long long left = N - pos;
@@ -1307,7 +1308,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
         for (int t = 0; t < PH_COUNT; ++t) sh.prof[t] = 0;
         sh.prof_last = clock64();
         sh.mode = (p.engine == 2) ? 1 : ((p.engine == 1) ? 0 : (p.init_gap >= GAP_TO_WIN ? 1 : 0));
-        sh.win = f_next_window(p.init_gap, p.start_pos, p.N);
+        sh.win = f_next_window(p.init_gap, p.start_pos, p.N, p.win_factor);
         const uint32_t mb = smem_u32(&sh.mbar);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1383,7 +1384,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
                 sh.pos = pos + done;
                 sh.dall_ver = sh.ver;   // several changes since the evaluators last looked
                 if (p.engine == 0 && sh.gap >= GAP_TO_WIN) sh.mode = 1;
-                sh.win = f_next_window(sh.gap, sh.pos, p.N);
+                sh.win = f_next_window(sh.gap, sh.pos, p.N, p.win_factor);
             }
         } else {
             const unsigned int r = sh.round;
@@ -1453,7 +1454,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
                 sh.windows += 1;
                 sh.round = r + 1u;
                 if (p.engine == 0 && sh.gap < GAP_TO_SEQ) sh.mode = 0;
-                sh.win = f_next_window(sh.gap, sh.pos, p.N);
+                sh.win = f_next_window(sh.gap, sh.pos, p.N, p.win_factor);
             }
         }
         __syncthreads();
