@@ -134,6 +134,21 @@ int bgmm_log_marg_k(bgmm_t *h, double *out);
 /* replaces: IGMM.log_marg (igmm/igmm.py:199-215) with the CRP term evaluated with libm lgamma */
 int bgmm_log_marg(bgmm_t *h, double alpha, double *out);
 
+/*
+ * replaces: the clustering metrics of GMM.update_record_dict (gmm/gmm.py:81-106) -- normalized_mutual_information,
+ * mutual_information, information_variation (infopy/infopy.py:31-119: one pass over the data per (true, predicted)
+ * cell) and utils.cluster_loss_inertia (utils/utils.py:31-88) -- by ONE device pass over the labels:
+ *   bgmm_set_true_labels  uploads the ground-truth labels once (values in [0, T));
+ *   bgmm_contingency      table[t * (K + 1) + k] = #{i: true[i] == t, assignments[i] == k}; column K counts the
+ *                         unassigned (-1) data.  T x (K + 1) int64, row-major.  Every metric above is a function of it.
+ *   bgmm_cluster_ssq      out[k] = sum over members of component k of |x_i - mean_k|^2 (utils.py:52-88 takes the
+ *                         square root and truncates to an integer), from the sufficient statistics; K entries.
+ * The labels never leave the device.
+ */
+int bgmm_set_true_labels(bgmm_t *h, const int64_t *t /* N */, int32_t T);
+int bgmm_contingency(bgmm_t *h, int64_t *table /* T * (K + 1) */);
+int bgmm_cluster_ssq(bgmm_t *h, double *out /* K */);
+
 /* replaces: add_item(i,k) (gaussian_components.py:154-169) and del_item(i) (:171-186, incl. del_component :188-205) */
 int bgmm_add_item(bgmm_t *h, int64_t i, int32_t k);
 int bgmm_del_item(bgmm_t *h, int64_t i);

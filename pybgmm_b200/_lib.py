@@ -20,6 +20,7 @@ EXPORTS = (
     "bgmm_set_assignments", "bgmm_sweep", "bgmm_sweep_dev", "bgmm_set_engine", "bgmm_seed", "bgmm_get_uniforms",
     "bgmm_sweep_index", "bgmm_get_state", "bgmm_get_assignments_dev", "bgmm_K", "bgmm_log_prior",
     "bgmm_log_post_pred", "bgmm_log_marg_k", "bgmm_log_marg", "bgmm_add_item", "bgmm_del_item", "bgmm_mt19937_fill",
+    "bgmm_set_true_labels", "bgmm_contingency", "bgmm_cluster_ssq",
 )
 
 
@@ -85,6 +86,9 @@ def lib():
     L.bgmm_add_item.argtypes = [vp, C.c_int64, C.c_int32]
     L.bgmm_del_item.argtypes = [vp, C.c_int64]
     L.bgmm_set_component_stats.argtypes = [vp, C.c_int32, dp, dp, C.c_int64]
+    L.bgmm_set_true_labels.argtypes = [vp, ip, C.c_int32]
+    L.bgmm_contingency.argtypes = [vp, ip]
+    L.bgmm_cluster_ssq.argtypes = [vp, dp]
     L.bgmm_mt19937_fill.argtypes = [C.POINTER(C.c_uint32), dp, C.c_int64]
     _LIB = L
     return L
@@ -246,6 +250,27 @@ class Chain(object):
         out = C.c_double()
         _check(lib().bgmm_log_marg(self._h, float(alpha), C.cast(C.byref(out), C.POINTER(C.c_double))))
         return out.value
+
+    def set_true_labels(self, labels):
+        """Upload ground-truth labels (any integers; they are ranked like np.unique does) for `contingency`."""
+        uniq, inv = np.unique(np.asarray(labels).ravel(), return_inverse=True)
+        if inv.shape != (self.N,):
+            raise ValueError("labels_true and labels_pred must have same size, got %d and %d" % (inv.size, self.N))
+        inv = np.ascontiguousarray(inv, dtype=np.int64)
+        _check(lib().bgmm_set_true_labels(self._h, _ip(inv), len(uniq)))
+        self.T_true = len(uniq)
+
+    def contingency(self):
+        """(T, K + 1) int64 table of (true label, component); the last column counts unassigned data."""
+        out = np.empty((self.T_true, self.K + 1), np.int64)
+        _check(lib().bgmm_contingency(self._h, _ip(out)))
+        return out
+
+    def cluster_ssq(self):
+        """Per component: sum of squared distances of its members to their mean (from the statistics)."""
+        out = np.empty(max(self.K, 1), np.float64)
+        _check(lib().bgmm_cluster_ssq(self._h, _dp(out)))
+        return out[:self.K]
 
     def add_item(self, i, k):
         _check(lib().bgmm_add_item(self._h, int(i), int(k)))

@@ -63,6 +63,75 @@ __global__ void k_philox(double *__restrict__ u, long long N, unsigned long long
     if (j < N) u[j] = philox_uniform(seed, sweep, (unsigned long long)j);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-sweep record (GMM.update_record_dict, gmm/gmm.py:65-118) without moving the labels to the host.
+//
+// k_contingency: table[t][k] = #{i : true_label[i] == t and datum i sits in component slot k}, column K = unassigned.
+// This is the one O(N) pass behind nmi / mi / vi (infopy/infopy.py:62-119 makes a pass over the data per CELL).
+// HBM-bound integer work: 8 B per datum (two int32 labels, 16-B vector loads, grid-stride, a multiple of the SM
+// count of CTAs); counts go to a CTA-private shared-memory table (32-bit, a CTA sees < 2^31 data) that is folded
+// into the global 64-bit table with one atomic per non-zero cell; tables too large for shared memory take global
+// atomics directly (they live in L2).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_contingency(const int *__restrict__ t_true, const int *__restrict__ z_uid,
+                              const int *__restrict__ slot_of_uid, long long N, int T, int K, int in_smem,
+                              unsigned long long *__restrict__ table) {
+    extern __shared__ __align__(16) unsigned int cell[];
+    const int C = K + 1, cells = T * C;
+    if (in_smem) {
+        for (int e = threadIdx.x; e < cells; e += blockDim.x) cell[e] = 0u;
+        __syncthreads();
+    }
+    const long long nvec = N >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec + 1; v += stride) {
+        int tt[4], uu[4], n = 4;
+        if (v < nvec) {
+            const int4 a = __ldg(reinterpret_cast<const int4 *>(t_true) + v);
+            const int4 b = __ldcs(reinterpret_cast<const int4 *>(z_uid) + v);
+            tt[0] = a.x; tt[1] = a.y; tt[2] = a.z; tt[3] = a.w;
+            uu[0] = b.x; uu[1] = b.y; uu[2] = b.z; uu[3] = b.w;
+        } else {  // the ragged tail (N % 4 data), taken by exactly one thread
+            n = (int)(N & 3);
+            for (int q = 0; q < n; ++q) { tt[q] = t_true[(nvec << 2) + q]; uu[q] = z_uid[(nvec << 2) + q]; }
+        }
+        for (int q = 0; q < n; ++q) {
+            const int k = uu[q] < 0 ? K : __ldg(slot_of_uid + uu[q]);
+            const int e = tt[q] * C + k;
+            if (in_smem) atomicAdd(cell + e, 1u);
+            else atomicAdd(table + e, 1ULL);
+        }
+    }
+    if (in_smem) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < cells; e += blockDim.x) {
+            const unsigned int c = cell[e];
+            if (c) atomicAdd(table + e, (unsigned long long)c);
+        }
+    }
+}
+
+// k_cluster_ssq: out[k] = sum_i |x_i - mean_k|^2 over the members of component k -- the quantity under the square
+// root of utils.compute_dist (utils/utils.py:52-88) -- from the sufficient statistics alone:
+//   sum_a [ sum x_a^2 - (sum x_a)^2 / n ],  sum x_a = num_a - k0 m0_a,  sum x_a^2 = S_aa - (S0_aa + k0 m0_a^2).
+// One warp per component; no pass over the data.
+template <int COV>
+__global__ void k_cluster_ssq(const Params p, int DP, double *__restrict__ out) {
+    const int k = blockIdx.x, lane = threadIdx.x & 31;
+    const int SS = stat_len(DP, COV);
+    const double n = (double)p.counts[k];
+    double acc = 0.0;
+    for (int a = lane; a < p.D; a += 32) {
+        const int e = (COV == COV_FULL) ? row_idx(a, a) : a;
+        const double base = __dadd_rn(p.S0[e], __dmul_rn(p.k0, __dmul_rn(p.m0[a], p.m0[a])));
+        const double sxx = p.S[(size_t)k * SS + e] - base;
+        const double sx = p.num[(size_t)k * DP + a] - __dmul_rn(p.k0, p.m0[a]);
+        acc += sxx - sx * sx / n;
+    }
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[k] = acc > 0.0 ? acc : 0.0;
+}
+
 // log_marg_k for every live component (gaussian_components.py:253-276 / _diag.py:271-289); one warp each
 template <int COV>
 __global__ void k_log_marg_k(const Params p, int DP, double logdet_S0, double *__restrict__ out) {
@@ -206,6 +275,7 @@ static void free_all(bgmm_handle *h) {
     cudaFree(h->d_counts); cudaFree(h->d_num); cudaFree(h->d_S); cudaFree(h->d_rec); cudaFree(h->d_wbuf);
     cudaFree(h->d_rec_prior); cudaFree(h->d_ctl); cudaFree(h->d_err); cudaFree(h->d_u); cudaFree(h->d_order);
     cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf); cudaFree(h->d_ntab); cudaFree(h->d_fmtab);
+    cudaFree(h->d_true); cudaFree(h->d_table);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
@@ -783,6 +853,71 @@ int bgmm_log_marg(bgmm_t *h, double alpha, double *out) {
     double lpx = 0.0;
     for (int k = 0; k < K; ++k) lpx += lk[k];
     *out = lpz + lpx;
+    return 0;
+}
+
+int bgmm_set_true_labels(bgmm_t *h, const int64_t *t, int32_t T) {
+    if (!h || !t) return fail(BGMM_EINVAL, "NULL argument");
+    if (T < 1) return fail(BGMM_EINVAL, "T must be >= 1");
+    std::vector<int> t32((size_t)h->N);
+    for (long long i = 0; i < h->N; ++i) {
+        if (t[i] < 0 || t[i] >= T) return fail(BGMM_EINVAL, "true label out of range [0, T)");
+        t32[(size_t)i] = (int)t[i];
+    }
+    CU(cudaSetDevice(h->device));
+    if (!h->d_true) CU(cudaMalloc((void **)&h->d_true, sizeof(int) * (size_t)(h->N + 4)));
+    CU(cudaMemcpyAsync(h->d_true, t32.data(), sizeof(int) * (size_t)h->N, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->T_true = T;
+    return 0;
+}
+
+int bgmm_contingency(bgmm_t *h, int64_t *table) {
+    if (!h || !table) return fail(BGMM_EINVAL, "NULL argument");
+    if (!h->d_true) return fail(BGMM_EINVAL, "bgmm_set_true_labels has not been called");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int T = h->T_true, K = h->K;
+    const size_t cells = (size_t)T * (K + 1);
+    if (cells > h->table_cells) {
+        cudaFree(h->d_table);
+        h->d_table = nullptr;
+        h->table_cells = 0;
+        CU(cudaMalloc((void **)&h->d_table, sizeof(unsigned long long) * cells));
+        h->table_cells = cells;
+    }
+    CU(cudaMemsetAsync(h->d_table, 0, sizeof(unsigned long long) * cells, st));
+    const int TB = 256;
+    const size_t smem = sizeof(unsigned int) * cells;
+    const int in_smem = smem <= (size_t)200 * 1024;
+    if (in_smem && smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(k_contingency, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // a multiple of the SM count; fewer CTAs when the table is large (every CTA clears and folds its own copy)
+    const long long want = ((h->N >> 2) + TB) / TB;
+    const int per_sm = smem <= 32 * 1024 ? 4 : 1;
+    const int grid = (int)std::max(1LL, std::min(want, (long long)h->num_sms * per_sm));
+    k_contingency<<<grid, TB, in_smem ? smem : 0, st>>>(h->d_true, h->d_z, h->d_slot_of_uid, h->N, T, K, in_smem,
+                                                          h->d_table);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(table, h->d_table, sizeof(unsigned long long) * cells, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bgmm_cluster_ssq(bgmm_t *h, double *out) {
+    if (!h || !out) return fail(BGMM_EINVAL, "NULL argument");
+    if (h->K == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    double *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_out, sizeof(double) * h->K));
+    Params p = make_params(h);
+    if (h->cov == BGMM_COV_FULL) k_cluster_ssq<COV_FULL><<<h->K, 32, 0, st>>>(p, h->DP, d_out);
+    else k_cluster_ssq<COV_DIAG><<<h->K, 32, 0, st>>>(p, h->DP, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out, sizeof(double) * h->K, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_out);
     return 0;
 }
 

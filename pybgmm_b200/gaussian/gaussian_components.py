@@ -33,6 +33,8 @@ class _DeviceComponents(object):
         self._chain = _lib.Chain(X, prior.m_0, prior.k_0, prior.v_0, prior.S_0, self.K_max,
                                  covariance_type=self._COV, device=device)
         self._cache = None
+        self._labels = None
+        self._true_ref = None
         self._log_prior = None
         if assignments is None:
             z = -1 * np.ones(self.N, np.int64)
@@ -53,12 +55,14 @@ class _DeviceComponents(object):
 
     # ---- lazily synchronised views ------------------------------------------------------------
     def _state(self):
+        """Counts and per-component statistics (K_max-sized arrays; the N labels are fetched separately)."""
         if self._cache is None:
-            self._cache = self._chain.get_state()
+            self._cache = self._chain.get_state(z=False)
         return self._cache
 
     def _dirty(self):
         self._cache = None
+        self._labels = None
 
     @property
     def chain(self):
@@ -71,7 +75,21 @@ class _DeviceComponents(object):
 
     @property
     def assignments(self):
-        return self._state()["z"]
+        if self._labels is None:
+            self._labels = self._chain.assignments()
+        return self._labels
+
+    # ---- per-sweep record on the device (no label traffic) ---------------------------------------
+    def contingency(self, true_assignments):
+        """(T, K + 1) table of (rank of the true label, component); last column = unassigned.  The true labels are
+        uploaded the first time a given vector is seen."""
+        if self._true_ref is not true_assignments:
+            self._chain.set_true_labels(true_assignments)
+            self._true_ref = true_assignments
+        return self._chain.contingency()
+
+    def cluster_ssq(self):
+        return self._chain.cluster_ssq()
 
     @property
     def counts(self):

@@ -27,12 +27,27 @@ class GMM(object):
     def setup_record_dict(self):
         return dict((key, []) for key in RECORD_KEYS)
 
+    #: "device": the contingency table and the per-cluster squared distances come from the GPU (bgmm_contingency,
+    #: bgmm_cluster_ssq; the labels stay there); "host": both are recounted from the labels with NumPy.
+    metrics_backend = "device"
+
     def _clustering_metrics(self, true_assignments):
-        z = self.components.assignments
-        loss = utils.cluster_loss_inertia(self.components.X, z)
-        return {"nmi": normalized_mutual_information(true_assignments, z),
-                "mi": mutual_information(true_assignments, z),
-                "vi": information_variation(true_assignments, z, base=2),
+        comps = self.components
+        table = None
+        if self.metrics_backend == "device":
+            table = comps.contingency(true_assignments)
+            if table[:, -1].any():
+                table = None          # unassigned data form a cluster of their own in the reference: count on the host
+        if table is not None:
+            table = table[:, :-1]
+            loss = utils.cluster_loss_from_ssq(comps.cluster_ssq())
+            z = None
+        else:
+            z = comps.assignments
+            loss = utils.cluster_loss_inertia(comps.X, z)
+        return {"nmi": normalized_mutual_information(true_assignments, z, table=table),
+                "mi": mutual_information(true_assignments, z, table=table),
+                "vi": information_variation(true_assignments, z, base=2, table=table),
                 "loss": loss,
                 "bic": loss}   # the reference files the inertia loss under "bic" as well (gmm.py:99-101)
 

@@ -1,8 +1,10 @@
 """Clustering metrics recorded once per sweep by GMM.update_record_dict (pybgmm/gmm/gmm.py:65-118).
 
 Same definitions as pybgmm/infopy/infopy.py:19-119 (entropy, mutual information, normalised mutual information,
-variation of information) but computed from one K_true x K contingency table in O(N) instead of the reference's
-O(K_true * K * N) Python loops, so they stay usable at N = 1e6.  Host-side reporting, not part of the hot path.
+variation of information) but computed from one K_true x K contingency table instead of the reference's
+O(K_true * K * N) Python loops, so they stay usable at N = 1e6.  Every function takes either the two label vectors
+(the table is then counted here, on the host) or `table=` -- the table counted on the device by
+`bgmm_contingency`, which is what the samplers' record keeping uses (the labels never leave the GPU).
 """
 import math
 
@@ -34,9 +36,9 @@ def entropy(x, base=math.e):
     return _entropy_counts(np.unique(x, return_counts=True)[1], base)
 
 
-def mutual_information(labels_true, labels_pred, normalized=False, base=math.e):
+def mutual_information(labels_true=None, labels_pred=None, normalized=False, base=math.e, table=None):
     """infopy.py:62-96 (the normaliser uses natural-log entropies whatever `base` is, as the reference does)."""
-    table = _contingency(labels_true, labels_pred)
+    table = _contingency(labels_true, labels_pred) if table is None else np.asarray(table)
     n = float(table.sum())
     px = table.sum(axis=1) / n
     py = table.sum(axis=0) / n
@@ -51,13 +53,13 @@ def mutual_information(labels_true, labels_pred, normalized=False, base=math.e):
     return mi
 
 
-def normalized_mutual_information(labels_true, labels_pred, base=math.e):
+def normalized_mutual_information(labels_true=None, labels_pred=None, base=math.e, table=None):
     """infopy.py:31-60."""
-    return mutual_information(labels_true, labels_pred, normalized=True, base=base)
+    return mutual_information(labels_true, labels_pred, normalized=True, base=base, table=table)
 
 
-def information_variation(labels_true, labels_pred, base=math.e):
+def information_variation(labels_true=None, labels_pred=None, base=math.e, table=None):
     """infopy.py:99-119."""
-    table = _contingency(labels_true, labels_pred)
+    table = _contingency(labels_true, labels_pred) if table is None else np.asarray(table)
     return (_entropy_counts(table.sum(axis=1), base) + _entropy_counts(table.sum(axis=0), base)
-            - 2 * mutual_information(labels_true, labels_pred, base=base))
+            - 2 * mutual_information(base=base, table=table))

@@ -30,3 +30,9 @@ def cluster_loss_inertia(x, assignments):
     unique_dist = np.zeros_like(uniq)
     unique_dist[:] = np.sqrt(ssq).astype(unique_dist.dtype)
     return np.sum(unique_dist)
+
+
+def cluster_loss_from_ssq(ssq):
+    """The same loss from the per-cluster sums of squared distances to the cluster mean (`bgmm_cluster_ssq`):
+    the square root of each, truncated to an integer like the reference's int array does, summed."""
+    return np.sum(np.sqrt(np.asarray(ssq, dtype=np.float64)).astype(np.int64))

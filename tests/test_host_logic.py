@@ -47,6 +47,24 @@ def test_metrics_against_golden():
         np.testing.assert_allclose(mutual_information(z_true, z), case["mi"], rtol=1e-10, atol=1e-13)
         np.testing.assert_allclose(information_variation(z_true, z, base=2), case["vi"], rtol=1e-10, atol=1e-12)
         assert float(utils.cluster_loss_inertia(X, z)) == case["loss"]
+        # the same metrics from a contingency table (what bgmm_contingency returns, without its unassigned column)
+        _, ti = np.unique(z_true, return_inverse=True)
+        K = int(z.max()) + 1
+        table = np.bincount(ti * K + z, minlength=(int(ti.max()) + 1) * K).reshape(-1, K)
+        assert normalized_mutual_information(table=table) == normalized_mutual_information(z_true, z)
+        assert mutual_information(table=table) == mutual_information(z_true, z)
+        assert information_variation(base=2, table=table) == information_variation(z_true, z, base=2)
+        # and the loss from the sufficient statistics (the arithmetic of k_cluster_ssq)
+        m_0, k_0, v_0, S_0 = cases.prior_for(case["D"], case["cov"], case["v_0"])
+        ssq = np.zeros(K)
+        for k in range(K):
+            xk = X[z == k]
+            num = k_0 * m_0 + xk.sum(axis=0)
+            s0d = np.diag(S_0) if np.ndim(S_0) == 2 else S_0
+            sdiag = (s0d + k_0 * m_0 * m_0) + np.square(xk).sum(axis=0)
+            sx = num - k_0 * m_0
+            ssq[k] = max(np.sum((sdiag - (s0d + k_0 * m_0 * m_0)) - sx * sx / len(xk)), 0.0)
+        assert float(utils.cluster_loss_from_ssq(ssq)) == case["loss"]
 
 
 def test_draw_is_the_reference_draw():
