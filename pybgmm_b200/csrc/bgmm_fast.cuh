@@ -163,6 +163,9 @@ struct FSh {
     int dlog_a[DLOG], dlog_b[DLOG];  // components touched by the change into version v, at index v % DLOG
     unsigned int round;
     unsigned long long mbar;
+    // CTA-wide draw of f_step: inclusive totals, first hit and its margin per warp (4 warps x 32 choices)
+    double wtot[4], wmg[4];
+    int wcand[4];
     long long prof[PH_COUNT], prof_last;
 };
 
@@ -409,6 +412,72 @@ __device__ __noinline__ void f_eval_rows2(const double *__restrict__ rec, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// f_step's evaluation for D = 16 and K + 1 <= 128: the quadratic form of ONE component is split over four threads that
+// sit in four different warps (warp-uniform PART, lanes over components: no divergence, conflict-free loads), so all
+// 16 warps work on the one datum of a sequential step instead of 4.  d^T B d over the packed lower triangle, rows and
+// columns split in halves L = 0..7, H = 8..15:
+//   PART 0: block LL (36 terms)   PART 1: block HH (36)   PART 2: rows 8..11 x L (32)   PART 3: rows 12..15 x L (32)
+// returns this part of  sum_a d_a (sum_{b<a} B_ab d_b + B_aa d_a / 2);  q = 2 * (sum of the four).  Same formula as
+// f_eval_lane, different summation order (agreement to rounding).
+// ---------------------------------------------------------------------------------------------
+template <int PART, int ST>
+__device__ __forceinline__ double f_quad_part16(const double *__restrict__ col, const double *__restrict__ x) {
+    using Ly = Lay<16>;
+    double q = 0.0;
+    if constexpr (PART <= 1) {
+        constexpr int O = PART * 8;
+        double d[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) d[a] = col[(Ly::MU + O + a) * ST] - x[O + a];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int ra = (O + a) * (O + a + 1) / 2 + O;   // packed index of element (O + a, O)
+            double r = 0.0;
+#pragma unroll
+            for (int b = 0; b < a; ++b) r = fma(col[(ra + b) * ST], d[b], r);
+            r = fma(0.5 * col[(ra + a) * ST], d[a], r);
+            q = fma(d[a], r, q);
+        }
+    } else {
+        constexpr int O = 8 + (PART - 2) * 4;
+        double dl[8], dh[4];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) dl[b] = col[(Ly::MU + b) * ST] - x[b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) dh[a] = col[(Ly::MU + O + a) * ST] - x[O + a];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int ra = (O + a) * (O + a + 1) / 2;       // packed index of element (O + a, 0)
+            double r = 0.0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) r = fma(col[(ra + b) * ST], dl[b], r);
+            q = fma(dh[a], r, q);
+        }
+    }
+    return q;
+}
+
+// exp(weight - wref) from the quadratic form q (the tail of f_eval_lane); NaN when the closed form of the own
+// component is not trusted
+template <int ST>
+__device__ __forceinline__ double f_finish_weight(const double *__restrict__ sc, double q, int own, double wref,
+                                                  const double *__restrict__ fmtab) {
+    double arg, hh, cc;
+    if (own) {
+        arg = 1.0 - sc[F_BETA * ST] * q;
+        if (!(arg > OM_MIN)) return NAN;
+        hh = 1.0 - sc[F_H * ST];
+        cc = sc[F_CWO * ST];
+    } else {
+        arg = 1.0 + sc[F_G * ST] * q;
+        hh = sc[F_H * ST];
+        cc = sc[F_CW * ST];
+    }
+    const double t = (cc - hh * fm::f_log(arg, fmtab)) - wref;
+    return (t < EXP_CUTOFF) ? 0.0 : fm::f_exp(t, fmtab);
+}
+
+// ---------------------------------------------------------------------------------------------
 // draw (utils.py:7-20) by one warp from the n = K + 1 unnormalised probabilities e[] in shared memory: the first
 // index whose inclusive cumulative sum exceeds u * total, else the last index.  Lane l owns the nb consecutive
 // entries starting at l * nb.  Returns the index, or -2 when the total is not finite / positive (the caller falls
@@ -598,20 +667,25 @@ __device__ __noinline__ void f_rank_one_warp(const Params &p, const FSmem<DP> &s
     double sq = dr * acc;
 #pragma unroll
     for (int o = DP / 2; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if (lane < 2 * NT_W) nt[lane] = ntv;
     __syncwarp();
     // beta = kappa / (kappa -+ 1): BETA(n) for a removal, G(n) for an addition
     const double beta = (sign < 0) ? sc[F_BETA * ST] : sc[F_G * ST];
     const double den = (sign < 0) ? 1.0 - beta * sq : 1.0 + beta * sq;
     const double gam = (sign < 0) ? beta / den : -beta / den;
-    const double rk2 = nt[NT_W + NT_RK];   // 1 / kappa(n2)
     const double lg_den = log(den);        // every lane: overlaps the matrix update below instead of trailing it
-#pragma unroll 1
-    for (int e = lane; e < Ly::PP; e += 32) {
-        const int a = s.rc[e] >> 8, b = s.rc[e] & 0xff;
-        double *pe = col + e * ST;
-        *pe = fma(gam * vv[a], vv[b], *pe);
+#pragma unroll
+    for (int e0 = 0; e0 < Ly::PP; e0 += 32) {
+        const int e = e0 + lane;
+        if (e < Ly::PP) {
+            const int a = s.rc[e] >> 8, b = s.rc[e] & 0xff;
+            double *pe = col + e * ST;
+            *pe = fma(gam * vv[a], vv[b], *pe);
+        }
     }
+    // the count-table rows (an L2 round trip issued at the top) are first needed here
+    if (lane < 2 * NT_W) nt[lane] = ntv;
+    __syncwarp();
+    const double rk2 = nt[NT_W + NT_RK];   // 1 / kappa(n2)
     if (part == 0) {
         double *pm = col + (Ly::MU + r) * ST;
         *pm = fma((sign < 0) ? -dr : dr, rk2, *pm);
@@ -879,13 +953,58 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
     const double wref = p.log_alpha + s.lpb[jj];   // the new-table weight (crpmm.py:74) is the exp scale
     const bool own_live = (k_old >= 0) && !died;
 
-    // phase A: exp(weight - wref) of every live component (crpmm.py:68-75), thread k evaluates component k
-    if (tid < K) {
-        const double e = f_eval_lane<DP, ST>(s.rec + tid, xs, (own_live && tid == k_old) ? 1 : 0, wref, 0, p.fmtab);
-        if (e != e) sh.need_explicit = seq;
-        ew[tid] = e;
-    } else if (tid == K) {
-        ew[K] = 1.0;
+    // phase A: exp(weight - wref) of every live component (crpmm.py:68-75)
+    bool cta_draw = false;   // the K + 1 choices sit one per thread in warps 0..3 (uniform over the CTA)
+    double e_mine = 0.0, incl = 0.0;
+    if constexpr (DP == 16) {
+        if (K < 128) {
+            // four threads per component, one in each quarter of the CTA (f_quad_part16); partial sums of parts
+            // 1..3 through the refactor scratch (A and W are contiguous: 392 doubles, idle outside the rare paths)
+            cta_draw = true;
+            double *psum = s.A;
+            const int k = tid & 127, part = warp >> 2;
+            double pq = 0.0;
+            if (k < K) {
+                const double *col = s.rec + k;
+                switch (part) {
+                    case 0: pq = f_quad_part16<0, ST>(col, xs); break;
+                    case 1: pq = f_quad_part16<1, ST>(col, xs); break;
+                    case 2: pq = f_quad_part16<2, ST>(col, xs); break;
+                    default: pq = f_quad_part16<3, ST>(col, xs); break;
+                }
+                if (part > 0) psum[(part - 1) * 128 + k] = pq;
+            }
+            __syncthreads();
+            if (warp < 4) {
+                if (tid < K) {
+                    const double q = 2.0 * ((pq + psum[tid]) + (psum[128 + tid] + psum[256 + tid]));
+                    e_mine = f_finish_weight<ST>(s.rec + tid + Ly::SC * ST, q, (own_live && tid == k_old) ? 1 : 0, wref,
+                                                 p.fmtab);
+                    if (e_mine != e_mine) sh.need_explicit = seq;
+                } else if (tid == K) {
+                    e_mine = 1.0;
+                }
+                ew[tid] = e_mine;   // for the rare paths
+                // inclusive scan of this warp's 32 choices, straight from the registers
+                incl = e_mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane == 31) sh.wtot[warp] = incl;
+            }
+        }
+    }
+    if (!cta_draw) {
+        // thread k evaluates component k
+        if (tid < K) {
+            const double e = f_eval_lane<DP, ST>(s.rec + tid, xs, (own_live && tid == k_old) ? 1 : 0, wref, 0, p.fmtab);
+            if (e != e) sh.need_explicit = seq;
+            ew[tid] = e;
+        } else if (tid == K) {
+            ew[K] = 1.0;
+        }
     }
     __syncthreads();
     F_PROF(PH_EVAL);
@@ -893,14 +1012,37 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
     if (sh.need_explicit == seq) {
         f_explicit_own<DP>(p, s, k_old, n_old, xs, wref, ew, seq);
         expl = (sh.explicit_done == seq);
+        cta_draw = false;   // ew[k_old] changed: the one-warp draw below reads ew[]
         F_PROF(PH_RARE);
     }
 
-    // phase B: the draw (crpmm.py:75-78, utils.py:7-20)
-    if (warp == 0) {
-        double mg;
-        const int k = f_warp_pick(ew, K + 1, s.ub[jj], &mg);
-        if (lane == 0) {
+    // phase B: the draw (crpmm.py:75-78, utils.py:7-20): first index whose cumulative sum exceeds u * total
+    int k_drawn;
+    if (cta_draw) {
+        const double w0 = sh.wtot[0], w1 = sh.wtot[1], w2 = sh.wtot[2], w3 = sh.wtot[3];
+        const double p1 = w0, p2 = w0 + w1, p3 = p2 + w2, tot = p3 + w3;
+        const double t0 = s.ub[jj] * tot;
+        if (warp < 4) {
+            const double pre = (warp == 0) ? 0.0 : (warp == 1) ? p1 : (warp == 2) ? p2 : p3;
+            double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 0.0;
+            const double upper = pre + incl, lower = pre + excl;   // lower == the previous choice's upper, bit for bit
+            const unsigned who = __ballot_sync(0xffffffffu, upper > t0);
+            if (who != 0u && lane == __ffs(who) - 1) {
+                sh.wcand[warp] = tid;
+                sh.wmg[warp] = (double)__fdividef((float)fmin(t0 - lower, upper - t0), (float)tot);
+            } else if (who == 0u && lane == 0) {
+                sh.wcand[warp] = 1 << 20;
+            }
+        }
+        __syncthreads();
+        int k = min(min(sh.wcand[0], sh.wcand[1]), min(sh.wcand[2], sh.wcand[3]));
+        double mg = 0.0;
+        if (k > K) k = K;                       // utils.py:20 fallback: the last index (also absorbs the zero padding)
+        else mg = sh.wmg[k >> 5];
+        if (!(tot > 0.0) || !(tot < INFINITY)) k = -2;
+        k_drawn = k;
+        if (tid == 0) {
             sh.k_new = k;
             if (k >= 0) {
                 sh.evals += K;
@@ -908,13 +1050,31 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
                 if (mb < sh.margin_bits) sh.margin_bits = mb;
             }
         }
+    } else {
+        if (warp == 0) {
+            double mg;
+            const int k = f_warp_pick(ew, K + 1, s.ub[jj], &mg);
+            if (lane == 0) {
+                sh.k_new = k;
+                if (k >= 0) {
+                    sh.evals += K;
+                    const unsigned long long mb = (unsigned long long)__double_as_longlong(mg);
+                    if (mb < sh.margin_bits) sh.margin_bits = mb;
+                }
+            }
+        }
+        __syncthreads();
+        k_drawn = sh.k_new;
     }
-    __syncthreads();
-    if (sh.k_new == -2) f_log_domain_draw<DP>(p, s, K, k_old, own_live, expl, xs, wref, s.ub[jj], ew);
+    if (k_drawn == -2) {
+        if (cta_draw) __syncthreads();   // thread 0's sh.k_new = -2 must not land after the fallback's result
+        f_log_domain_draw<DP>(p, s, K, k_old, own_live, expl, xs, wref, s.ub[jj], ew);
+        k_drawn = sh.k_new;
+    }
     F_PROF(PH_DRAW);
     F_COUNT(PH_STEPS);
     if (sh.error) return;
-    const int k_new = sh.k_new;
+    const int k_new = k_drawn;
     if (k_new == k_old && !died) return;  // stay: nothing was touched (crpmm.py:82-85)
 
     // phase C: the datum moves: add_item (gaussian_components.py:154-169)

@@ -1,0 +1,8 @@
+#!/bin/bash
+# parity suite + a 4-sweep cold C3 probe (what a change of the sweep engine is checked with)
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log
+timeout 300 python tools/perf_probe.py --sweeps ${SWEEPS:-4} > gpurun_out/probe.log 2>&1; echo "probe rc=$?"
+grep -o "^sweep [0-9]*\|'moves': [0-9]*\|'windows': [0-9]*\|'seq_data': [0-9]*\|'sweep_kernel_ms': [0-9.]*" gpurun_out/probe.log | paste - - - - - 
+grep phases gpurun_out/probe.log | head -3 | cut -c1-400
