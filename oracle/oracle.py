@@ -255,3 +255,21 @@ def run_pcrpmm(orc, n_iter, alpha, n_power=1.01, power_burnin=0, flag_power=True
         use_power = flag_power and i_iter > power_burnin
         stats.append(orc.sweep(u, alpha, order=order, logcount_tab=tab if use_power else None))
     return stats
+
+
+def run_adapcrpmm(orc, n_iter, alpha, r_up=1.3, adapcrp_perct=0.04, adapcrp_burnin=0, flag_adapcrp=True):
+    """adapcrpmm.py:83-157 with num_saved=0: the power is recomputed before every sweep from the cluster sizes
+    (:100-104), random scan whenever it exceeds 1 (:110-115).  Burn-in sweeps (where the reference itself stops with
+    UnboundLocalError, :110) run as plain CRP sweeps, as its docstring describes."""
+    stats = []
+    for i_iter in range(n_iter):
+        power = 1.0
+        if flag_adapcrp and i_iter > adapcrp_burnin:
+            n_k = np.array(orc.counts[:orc.K])
+            small = len(n_k[np.where(n_k <= orc.N * adapcrp_perct)[0]]) * 1.0 / len(n_k)
+            power = 1.0 + (r_up - 1.0) * small
+        order = np.random.permutation(range(orc.N)) if (flag_adapcrp and power > 1) else None
+        u = np.array([random.random() for _ in range(orc.N)])
+        use_power = flag_adapcrp and i_iter > adapcrp_burnin
+        stats.append(orc.sweep(u, alpha, order=order, logcount_tab=logcount_table(orc.N, power) if use_power else None))
+    return stats

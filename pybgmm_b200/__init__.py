@@ -1,5 +1,5 @@
 """pybgmm_b200 -- B200-native collapsed-Gibbs sampler for the CRP / pCRP Gaussian mixture model behind the class
-surface of junlulocky/PyBGMM (NIW, GaussianComponents{,Diag}, IGMM / CRPMM / PCRPMM).
+surface of junlulocky/PyBGMM (NIW, GaussianComponents{,Diag}, IGMM / CRPMM / PCRPMM / ADAPCRPMM).
 
 The package layout mirrors the reference's (`pybgmm.prior`, `pybgmm.gaussian`, `pybgmm.gmm`, `pybgmm.igmm`,
 `pybgmm.utils`), so switching is a change of the top-level package name.  All arithmetic of the hot path runs in
@@ -8,7 +8,7 @@ libbgmm_b200.so (hand-written sm_100a CUDA); there is no CPU fallback.
 from .prior import NIW
 from .gaussian import GaussianComponents, GaussianComponentsDiag
 from .gmm import GMM
-from .igmm import IGMM, CRPMM, PCRPMM
+from .igmm import IGMM, CRPMM, PCRPMM, ADAPCRPMM
 
-__all__ = ["NIW", "GaussianComponents", "GaussianComponentsDiag", "GMM", "IGMM", "CRPMM", "PCRPMM"]
+__all__ = ["NIW", "GaussianComponents", "GaussianComponentsDiag", "GMM", "IGMM", "CRPMM", "PCRPMM", "ADAPCRPMM"]
 __version__ = "0.1.0"

@@ -34,6 +34,7 @@ class _DeviceComponents(object):
                                  covariance_type=self._COV, device=device)
         self._cache = None
         self._labels = None
+        self._counts = None
         self._true_ref = None
         self._log_prior = None
         if assignments is None:
@@ -63,6 +64,7 @@ class _DeviceComponents(object):
     def _dirty(self):
         self._cache = None
         self._labels = None
+        self._counts = None
 
     @property
     def chain(self):
@@ -93,7 +95,14 @@ class _DeviceComponents(object):
 
     @property
     def counts(self):
-        return self._state()["counts"]
+        """Cluster sizes (K_max int64, zero beyond K) -- fetched on their own: the per-sweep record and the adaptive
+        power schedule read them after every sweep and need nothing else."""
+        if self._cache is not None:
+            return self._cache["counts"]
+        if self._counts is None:
+            self._counts = self._chain.get_state(z=False, m_num=False, S_part=False, logdet=False,
+                                                 inv_covar=False)["counts"]
+        return self._counts
 
     @property
     def m_N_numerators(self):

@@ -26,8 +26,12 @@ K4_LOG_POST_PRED_K = -2.07325364088                                       # :104
 
 
 def golden():
+    """golden.json (CRPMM / PCRPMM / components) with the ADAPCRPMM cases of golden_adap.json appended."""
     with open(os.path.join(HERE, "golden", "golden.json")) as fh:
-        return json.load(fh)
+        gold = json.load(fh)
+    with open(os.path.join(HERE, "golden", "golden_adap.json")) as fh:
+        gold["samplers"] = gold["samplers"] + json.load(fh)["samplers"]
+    return gold
 
 
 def gen(N, D, K_true, seed):
@@ -57,6 +61,9 @@ def run_sampler_case_oracle(case):
     kw = case["kwargs"]
     if case["cls"] == "CRPMM":
         O.run_crpmm(orc, case["n_iter"], 1.0)
+    elif case["cls"] == "ADAPCRPMM":
+        O.run_adapcrpmm(orc, case["n_iter"], 1.0, r_up=kw.get("r_up", 1.3), adapcrp_perct=kw.get("adapcrp_perct", 0.04),
+                        adapcrp_burnin=kw.get("adapcrp_burnin", 0), flag_adapcrp=kw.get("flag_adapcrp", True))
     else:
         O.run_pcrpmm(orc, case["n_iter"], 1.0, n_power=kw.get("n_power", 1.01),
                      power_burnin=kw.get("power_burnin", 0), flag_power=kw.get("flag_power", True))

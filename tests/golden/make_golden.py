@@ -17,11 +17,12 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from oracle.make_ref import build as build_ref, import_ref  # noqa: E402
+from oracle.make_ref import build as build_ref, import_ref, import_ref_adapcrpmm  # noqa: E402
 
 if os.path.isdir("/root/reference/pybgmm"):
     build_ref("/root/reference", os.path.join(ROOT, "oracle", "_ref"))
 NIW, CRPMM, PCRPMM, GaussianComponents, GaussianComponentsDiag = import_ref()
+ADAPCRPMM = import_ref_adapcrpmm()
 
 
 def gen(N, D, K_true, seed):
@@ -118,6 +119,24 @@ def main():
     with open(os.path.join(HERE, "golden.json"), "w") as fh:
         json.dump(cases, fh)
     print("wrote", os.path.join(HERE, "golden.json"), os.path.getsize(os.path.join(HERE, "golden.json")), "bytes")
+    adaptive()
+
+
+def adaptive():
+    """ADAPCRPMM (pybgmm/igmm/adapcrpmm.py) cases, in their own file.  adapcrp_burnin=-1 throughout: the reference
+    stops with UnboundLocalError in its first sweep for any burn-in >= 0 (adapcrpmm.py:110)."""
+    A = []
+    A.append(sampler_case("adapcrpmm_2d", ADAPCRPMM, 200, 2, 4, 3, "full", "rand", 6, 8, adapcrp_burnin=-1))
+    A.append(sampler_case("adapcrpmm_2d_r2_perct10", ADAPCRPMM, 240, 2, 5, 11, "full", "rand", 12, 8, r_up=2.0,
+                          adapcrp_perct=0.1, adapcrp_burnin=-1))
+    A.append(sampler_case("adapcrpmm_diag_3d", ADAPCRPMM, 180, 3, 4, 12, "diag", "rand", 8, 6, r_up=1.5,
+                          adapcrp_perct=0.08, adapcrp_burnin=-1))
+    A.append(sampler_case("adapcrpmm_each_in_own", ADAPCRPMM, 60, 2, 3, 13, "full", "each-in-own", 1, 4,
+                          adapcrp_burnin=-1))
+    A.append(sampler_case("adapcrpmm_flag_off", ADAPCRPMM, 120, 2, 3, 14, "full", "rand", 4, 4, flag_adapcrp=False))
+    with open(os.path.join(HERE, "golden_adap.json"), "w") as fh:
+        json.dump({"samplers": A}, fh)
+    print("wrote golden_adap.json", len(A), "cases")
 
 
 if __name__ == "__main__":

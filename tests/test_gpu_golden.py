@@ -120,3 +120,21 @@ def test_errors_match_reference_conventions(gpu_lib):
         CRPMM(np.zeros((5, 2)), NIW(np.zeros(2), 1., 4, np.eye(2)), 1., None, covariance_type="bogus")
     with pytest.raises(AssertionError):                 # gaussian_components.py:103-105
         CRPMM(np.random.randn(5, 2), NIW(np.zeros(2), 1., 4, np.eye(2)), 1., None, assignments=np.array([0, 2, 2, 0, 0]))
+
+
+@pytest.mark.parametrize("burnin,flag", [(2, True), (0, True), (-1, True), (0, False)])
+def test_adapcrpmm_burnin_matches_oracle(gpu_lib, burnin, flag):
+    """ADAPCRPMM (adapcrpmm.py:83-157) beyond what the reference itself can run: burn-in sweeps (its own loop stops
+    with UnboundLocalError for adapcrp_burnin >= 0) are CRP sweeps, then the adaptive power; CUDA path vs oracle."""
+    case = dict(cls="ADAPCRPMM", N=150, D=2, K_true=4, seed=21, cov="full", assignments="rand", K_init=6, n_iter=6,
+                v_0=None, K_max=64, kwargs=dict(adapcrp_burnin=burnin, r_up=1.6, adapcrp_perct=0.1, flag_adapcrp=flag))
+    orc, z0, _ = cases.run_sampler_case_oracle(case)
+    model, rec, z0g = cases.run_sampler_case_gpu(case)
+    np.testing.assert_array_equal(z0g, z0)
+    np.testing.assert_array_equal(model.components.assignments, orc.assignments)
+    np.testing.assert_array_equal(model.components.counts[:model.components.K], orc.counts[:orc.K])
+    np.testing.assert_allclose(model.log_marg(), orc.log_marg(1.0), rtol=RTOL)
+    powers = model.adapcrp_powers
+    assert len(powers) == 6 and all(p == 1.0 for p in powers[:max(burnin + 1, 0)])
+    if not flag:
+        assert all(p == 1.0 for p in powers)
