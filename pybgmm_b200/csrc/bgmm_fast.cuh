@@ -702,6 +702,14 @@ __device__ __noinline__ void f_rank_one_warp(const Params &p, const FSmem<DP> &s
 
 // bit-exact statistics update in global memory by `nthr` threads of CTA 0 (thread rank t):
 // S -= / += fl(x_a x_b), num -= / += x_a   (gaussian_components.py:165-166, :184-185)
+// The addition is a fire-and-forget reduction performed by the L2 (RED.ADD.F64: one IEEE round-to-nearest add, the
+// same bits as __dadd_rn; v - o == v + (-o)), so the move phase of CTA 0 does not wait for an L2 round trip per
+// element.  Updates of one address are issued by different threads in different moves; they are ordered by the CTA
+// barriers between moves (coherence order of same-address atomics follows happens-before), and every reader of the
+// statistics sits behind a grid barrier or a CTA barrier.
+__device__ __forceinline__ void red_add_f64(double *addr, double v) {
+    asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
 template <int DP>
 __device__ __noinline__ void f_stats_axpy(const Params &p, const unsigned short *rc, int slot, const double *x, int sign,
                                           int init_prior, int t, int nthr) {
@@ -709,19 +717,27 @@ __device__ __noinline__ void f_stats_axpy(const Params &p, const unsigned short 
     const int D = p.D;
     double *S = p.S + (size_t)slot * Ly::PP;
     double *num = p.num + (size_t)slot * DP;
-#pragma unroll 1
+#pragma unroll 2
     for (int e = t; e < Ly::NS; e += nthr) {
         if (e < Ly::PP) {
             const int a = rc[e] >> 8, b = rc[e] & 0xff;
             if (a >= D) { if (init_prior) __stcg(S + e, 0.0); continue; }
             const double o = __dmul_rn(x[a], x[b]);
-            const double v = init_prior ? __dadd_rn(p.S0[e], __dmul_rn(p.k0, __dmul_rn(p.m0[a], p.m0[b]))) : __ldcg(S + e);
-            __stcg(S + e, sign > 0 ? __dadd_rn(v, o) : __dsub_rn(v, o));
+            if (init_prior) {
+                const double v = __dadd_rn(p.S0[e], __dmul_rn(p.k0, __dmul_rn(p.m0[a], p.m0[b])));
+                __stcg(S + e, sign > 0 ? __dadd_rn(v, o) : __dsub_rn(v, o));
+            } else {
+                red_add_f64(S + e, sign > 0 ? o : -o);
+            }
         } else {
             const int a = e - Ly::PP;
             if (a >= D) { if (init_prior) __stcg(num + a, 0.0); continue; }
-            const double v = init_prior ? __dmul_rn(p.k0, p.m0[a]) : __ldcg(num + a);
-            __stcg(num + a, sign > 0 ? __dadd_rn(v, x[a]) : __dsub_rn(v, x[a]));
+            if (init_prior) {
+                const double v = __dmul_rn(p.k0, p.m0[a]);
+                __stcg(num + a, sign > 0 ? __dadd_rn(v, x[a]) : __dsub_rn(v, x[a]));
+            } else {
+                red_add_f64(num + a, sign > 0 ? x[a] : -x[a]);
+            }
         }
     }
 }
@@ -935,7 +951,6 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
     constexpr int ST = Ly::KS;
     FSh &sh = *s.sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool cta0 = (blockIdx.x == 0);
     const double *xs = s.xb + jj * DP;
     double *ew = s.ew + (size_t)NWARP * Ly::WS;
 

@@ -10,5 +10,5 @@ nvcc $F -c pybgmm_b200/build/inst/inst_full_16.cu -o $B/full16.o &
 nvcc $F -c pybgmm_b200/build/inst/inst_diag_16.cu -o $B/diag16.o &
 g++ -O2 -fPIC -c pybgmm_b200/csrc/mt19937.cc -o $B/mt.o &
 wait
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o pybgmm_b200/lib/libbgmm_b200_prof.so $B/engine.o $B/full16.o $B/diag16.o $B/mt.o
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $B/lib.tmp $B/engine.o $B/full16.o $B/diag16.o $B/mt.o && mv $B/lib.tmp pybgmm_b200/lib/libbgmm_b200_prof.so
 echo built pybgmm_b200/lib/libbgmm_b200_prof.so
