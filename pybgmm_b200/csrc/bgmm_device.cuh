@@ -117,6 +117,8 @@ struct Params {
     double *ntab;             // count table: 8 doubles per count n = 0..N (bgmm_fast.cuh NT_*)
     int KS, Kcap;
     float win_factor;         // window length = win_factor x running gap between movers
+    int tune;                 // developer switches (env BGMM_TUNE): bit 0 = f_step evaluates with one thread per component,
+                              // bit 1 = statistics by load / add / store instead of L2 reductions
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -726,6 +726,9 @@ __device__ __noinline__ void f_stats_axpy(const Params &p, const unsigned short 
             if (init_prior) {
                 const double v = __dadd_rn(p.S0[e], __dmul_rn(p.k0, __dmul_rn(p.m0[a], p.m0[b])));
                 __stcg(S + e, sign > 0 ? __dadd_rn(v, o) : __dsub_rn(v, o));
+            } else if (p.tune & 2) {
+                const double v = __ldcg(S + e);
+                __stcg(S + e, sign > 0 ? __dadd_rn(v, o) : __dsub_rn(v, o));
             } else {
                 red_add_f64(S + e, sign > 0 ? o : -o);
             }
@@ -734,6 +737,9 @@ __device__ __noinline__ void f_stats_axpy(const Params &p, const unsigned short 
             if (a >= D) { if (init_prior) __stcg(num + a, 0.0); continue; }
             if (init_prior) {
                 const double v = __dmul_rn(p.k0, p.m0[a]);
+                __stcg(num + a, sign > 0 ? __dadd_rn(v, x[a]) : __dsub_rn(v, x[a]));
+            } else if (p.tune & 2) {
+                const double v = __ldcg(num + a);
                 __stcg(num + a, sign > 0 ? __dadd_rn(v, x[a]) : __dsub_rn(v, x[a]));
             } else {
                 red_add_f64(num + a, sign > 0 ? x[a] : -x[a]);
@@ -972,7 +978,7 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
     bool cta_draw = false;   // the K + 1 choices sit one per thread in warps 0..3 (uniform over the CTA)
     double e_mine = 0.0, incl = 0.0;
     if constexpr (DP == 16) {
-        if (K < 128) {
+        if (K < 128 && !(p.tune & 1)) {
             // four threads per component, one in each quarter of the CTA (f_quad_part16); partial sums of parts
             // 1..3 through the refactor scratch (A and W are contiguous: 392 doubles, idle outside the rare paths)
             cta_draw = true;

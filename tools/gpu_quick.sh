@@ -1,12 +1,17 @@
 #!/bin/bash
-# parity suite + a 4-sweep cold C3 probe (what a change of the sweep engine is checked with)
+# parity suite + a cold C3 probe (what a change of the sweep engine is checked with).  BGMM_TUNE selects code paths.
 mkdir -p gpurun_out
+export BGMM_TUNE=${TUNE:-0}
 timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log
 timeout 300 python tools/perf_probe.py --sweeps ${SWEEPS:-4} > gpurun_out/probe.log 2>&1; echo "probe rc=$?"
 grep -o "^sweep [0-9]*\|'moves': [0-9]*\|'windows': [0-9]*\|'seq_data': [0-9]*\|'sweep_kernel_ms': [0-9.]*" gpurun_out/probe.log | paste - - - - - 
-grep phases gpurun_out/probe.log | head -3 | cut -c1-400
 if [ -f pybgmm_b200/lib/libbgmm_b200_prof.so ]; then
   BGMM_B200_LIB=$PWD/pybgmm_b200/lib/libbgmm_b200_prof.so timeout 300 python tools/perf_probe.py --sweeps 4 > gpurun_out/probe_prof.log 2>&1
   grep "phases\|unit" gpurun_out/probe_prof.log | cut -c1-420
 fi
+for t in 1 2 3; do
+echo "--- BGMM_TUNE=$t"
+BGMM_TUNE=$t timeout 300 python tools/perf_probe.py --sweeps 3 > gpurun_out/probe_tune$t.log 2>&1
+grep -o "^sweep [0-9]*\|'moves': [0-9]*\|'sweep_kernel_ms': [0-9.]*" gpurun_out/probe_tune$t.log | paste - - -
+done
