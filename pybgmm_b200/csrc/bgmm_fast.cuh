@@ -484,14 +484,18 @@ __device__ __forceinline__ double f_finish_weight(const double *__restrict__ sc,
 // back to the log-domain draw).  *margin: distance of u to the nearest boundary of the drawn interval
 // (probability units, float accuracy -- a diagnostic).
 // ---------------------------------------------------------------------------------------------
+// The lane's (at most NB_MAX) entries are read once into registers: both passes below then run on registers, in the
+// same order as a loop over shared memory would (bit-identical sums; trailing zeros add nothing).
 static __device__ __noinline__ int f_warp_pick(const double *__restrict__ e, int n, double u, double *margin) {
     const int lane = threadIdx.x & 31;
     const int nb = (n + 31) >> 5;
     const int lo = lane * nb;
-    const int hi = min(n, lo + nb);
+    double v[NB_MAX];
+#pragma unroll
+    for (int t = 0; t < NB_MAX; ++t) v[t] = (t < nb && lo + t < n) ? e[lo + t] : 0.0;
     double run = 0.0;
-#pragma unroll 1
-    for (int t = lo; t < hi; ++t) run += e[t];
+#pragma unroll
+    for (int t = 0; t < NB_MAX; ++t) run += v[t];
     double incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -504,12 +508,14 @@ static __device__ __noinline__ int f_warp_pick(const double *__restrict__ e, int
     const double t0 = u * s;
     int cand = -1;
     double lower = excl, mg = 0.0, cum = 0.0;
-#pragma unroll 1
-    for (int t = lo; t < hi; ++t) {
-        cum += e[t];
-        const double upper = excl + cum;
-        if (upper > t0) { cand = t; mg = fmin(t0 - lower, upper - t0); break; }
-        lower = upper;
+#pragma unroll
+    for (int t = 0; t < NB_MAX; ++t) {
+        if (t < nb && lo + t < n && cand < 0) {
+            cum += v[t];
+            const double upper = excl + cum;
+            if (upper > t0) { cand = lo + t; mg = fmin(t0 - lower, upper - t0); }
+            else lower = upper;
+        }
     }
     const unsigned who = __ballot_sync(0xffffffffu, cand >= 0);
     int k;
