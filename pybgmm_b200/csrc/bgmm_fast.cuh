@@ -278,6 +278,16 @@ template <int DP> __device__ inline FSmem<DP> fast_carve(double *base, const Par
     return s;
 }
 
+// The FSmem pointers are generic (the struct is filled at run time), so loads through them are generic loads: they
+// go through the LSU's local/global path and wait on the long scoreboard.  On latency-critical single-warp paths the
+// same address is rebuilt from the kernel's dynamic shared array (the records start it), which the compiler can prove
+// to be shared memory: LDS / STS.
+template <int DP, class T> __device__ __forceinline__ T *f_sh(const FSmem<DP> &s, T *ptr) {
+    extern __shared__ __align__(16) double smem_raw[];
+    return reinterpret_cast<T *>(reinterpret_cast<char *>(smem_raw) +
+                                 (reinterpret_cast<const char *>(ptr) - reinterpret_cast<const char *>(s.rec)));
+}
+
 // ---------------------------------------------------------------------------------------------
 // count table: row n of Params::ntab (see the NT_* enum).  One thread per count; `with_fixed` also writes the
 // entries that do not depend on the power.
@@ -643,8 +653,11 @@ __device__ __noinline__ void f_rank_one_warp(const Params &p, const FSmem<DP> &s
     using Ly = Lay<DP>;
     constexpr int ST = Ly::KS;
     const int lane = threadIdx.x & 31;
-    double *col = s.rec + k;
-    double *dv = s.dv + which * DP, *vv = s.vv + which * DP, *nt = s.nt + which * 2 * NT_W;
+    double *col = f_sh<DP>(s, s.rec) + k;
+    double *dv = f_sh<DP>(s, s.dv) + which * DP, *vv = f_sh<DP>(s, s.vv) + which * DP;
+    double *nt = f_sh<DP>(s, s.nt) + which * 2 * NT_W;
+    const unsigned short *rc = f_sh<DP>(s, s.rc);
+    x = f_sh<DP>(s, x);   // the datum sits in the staging buffers (shared memory)
     double *sc = col + Ly::SC * ST;
     const double n = sc[F_N * ST];
     const double n2 = n + (double)sign;
@@ -678,12 +691,12 @@ __device__ __noinline__ void f_rank_one_warp(const Params &p, const FSmem<DP> &s
     const double beta = (sign < 0) ? sc[F_BETA * ST] : sc[F_G * ST];
     const double den = (sign < 0) ? 1.0 - beta * sq : 1.0 + beta * sq;
     const double gam = (sign < 0) ? beta / den : -beta / den;
-    const double lg_den = log(den);        // every lane: overlaps the matrix update below instead of trailing it
+    const double lg_den = fm::f_log(den, p.fmtab);   // den is om in (1/64, 1] or 1 + beta q >= 1
 #pragma unroll
     for (int e0 = 0; e0 < Ly::PP; e0 += 32) {
         const int e = e0 + lane;
         if (e < Ly::PP) {
-            const int a = s.rc[e] >> 8, b = s.rc[e] & 0xff;
+            const int a = rc[e] >> 8, b = rc[e] & 0xff;
             double *pe = col + e * ST;
             *pe = fma(gam * vv[a], vv[b], *pe);
         }
@@ -699,7 +712,7 @@ __device__ __noinline__ void f_rank_one_warp(const Params &p, const FSmem<DP> &s
     if (lane == 0) {
         const double cnt = sc[F_CNT * ST] + 1.0;
         f_write_scalars(sc, ST, n2, sc[F_LDS * ST] + lg_den, cnt, nt, nt + NT_W);
-        FSh &sh = *s.sh;
+        FSh &sh = *f_sh<DP>(s, s.sh);
         if (cnt >= (double)REFRESH_EVERY) { if (which == 0) sh.refresh_a = seq; else sh.refresh_b = seq; }
         if (which == 1) sh.moves += 1;
     }
@@ -908,7 +921,7 @@ __device__ __noinline__ void f_move_phase(const Params &p, const FSmem<DP> &s, i
                                           bool remove_now, bool birth, bool expl, bool died, int seq) {
     using Ly = Lay<DP>;
     constexpr int ST = Ly::KS;
-    FSh &sh = *s.sh;
+    FSh &sh = *f_sh<DP>(s, s.sh);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *xs = s.xb + jj * DP;
     if (warp == 0) {
@@ -961,23 +974,27 @@ template <int DP>
 __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj, int seq) {
     using Ly = Lay<DP>;
     constexpr int ST = Ly::KS;
-    FSh &sh = *s.sh;
+    FSh &sh = *f_sh<DP>(s, s.sh);   // shared-memory addressing on the step's dependent chain (see f_sh)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *xs = s.xb + jj * DP;
-    double *ew = s.ew + (size_t)NWARP * Ly::WS;
+    double *ew = f_sh<DP>(s, s.ew) + (size_t)NWARP * Ly::WS;
 
     // head: every thread derives the same values from the replicated state
-    const int uid = s.uidb[jj];
+    const int uid = f_sh<DP>(s, s.uidb)[jj];
     int k_old = -1;
     double n_old = 0.0;
-    if (uid >= 0) { k_old = s.slot_of_uid[uid]; n_old = s.rec[(Ly::SC + F_N) * ST + k_old]; }
+    if (uid >= 0) {
+        k_old = f_sh<DP>(s, s.slot_of_uid)[uid];
+        n_old = f_sh<DP>(s, s.rec)[(Ly::SC + F_N) * ST + k_old];
+    }
     bool died = false;
     if (k_old >= 0 && n_old == 1.0) {
         f_delete_component<DP>(p, s, k_old);
         died = true;
     }
     const int K = sh.K;
-    const double wref = p.log_alpha + s.lpb[jj];   // the new-table weight (crpmm.py:74) is the exp scale
+    const double wref = p.log_alpha + f_sh<DP>(s, s.lpb)[jj];   // the new-table weight (crpmm.py:74) is the exp scale
+    const double u_draw = f_sh<DP>(s, s.ub)[jj];
     const bool own_live = (k_old >= 0) && !died;
 
     // phase A: exp(weight - wref) of every live component (crpmm.py:68-75)
@@ -988,16 +1005,22 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
             // four threads per component, one in each quarter of the CTA (f_quad_part16); partial sums of parts
             // 1..3 through the refactor scratch (A and W are contiguous: 392 doubles, idle outside the rare paths)
             cta_draw = true;
-            double *psum = s.A;
+            // the records start the kernel's dynamic shared array: addressing everything through it (not through the
+            // generic pointers of FSmem) makes the loads below LDS -- all 16 warps load at once here, and generic
+            // loads queue in the LSU's local/global path (see f_bulk_eval)
+            extern __shared__ __align__(16) double smem_raw[];
+            const double *rec_sh = smem_raw;
+            const double *xs_sh = smem_raw + ((s.xb - s.rec) + jj * DP);
+            double *psum = smem_raw + (s.A - s.rec);
             const int k = tid & 127, part = warp >> 2;
             double pq = 0.0;
             if (k < K) {
-                const double *col = s.rec + k;
+                const double *col = rec_sh + k;
                 switch (part) {
-                    case 0: pq = f_quad_part16<0, ST>(col, xs); break;
-                    case 1: pq = f_quad_part16<1, ST>(col, xs); break;
-                    case 2: pq = f_quad_part16<2, ST>(col, xs); break;
-                    default: pq = f_quad_part16<3, ST>(col, xs); break;
+                    case 0: pq = f_quad_part16<0, ST>(col, xs_sh); break;
+                    case 1: pq = f_quad_part16<1, ST>(col, xs_sh); break;
+                    case 2: pq = f_quad_part16<2, ST>(col, xs_sh); break;
+                    default: pq = f_quad_part16<3, ST>(col, xs_sh); break;
                 }
                 if (part > 0) psum[(part - 1) * 128 + k] = pq;
             }
@@ -1005,7 +1028,7 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
             if (warp < 4) {
                 if (tid < K) {
                     const double q = 2.0 * ((pq + psum[tid]) + (psum[128 + tid] + psum[256 + tid]));
-                    e_mine = f_finish_weight<ST>(s.rec + tid + Ly::SC * ST, q, (own_live && tid == k_old) ? 1 : 0, wref,
+                    e_mine = f_finish_weight<ST>(rec_sh + tid + Ly::SC * ST, q, (own_live && tid == k_old) ? 1 : 0, wref,
                                                  p.fmtab);
                     if (e_mine != e_mine) sh.need_explicit = seq;
                 } else if (tid == K) {
@@ -1048,7 +1071,7 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
     if (cta_draw) {
         const double w0 = sh.wtot[0], w1 = sh.wtot[1], w2 = sh.wtot[2], w3 = sh.wtot[3];
         const double p1 = w0, p2 = w0 + w1, p3 = p2 + w2, tot = p3 + w3;
-        const double t0 = s.ub[jj] * tot;
+        const double t0 = u_draw * tot;
         if (warp < 4) {
             const double pre = (warp == 0) ? 0.0 : (warp == 1) ? p1 : (warp == 2) ? p2 : p3;
             double excl = __shfl_up_sync(0xffffffffu, incl, 1);

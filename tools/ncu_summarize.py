@@ -60,7 +60,7 @@ def main(rep, out):
     total = sum(x[0] for x in lines)
     with open(out + "_source_stalls.txt", "w") as fh:
         fh.write("warp-stall samples by source line (ncu --page source); total samples %d\n" % total)
-        for samp, ln, inst, st, text in lines[:60]:
+        for samp, ln, inst, st, text in lines[:200]:
             fh.write("%9d (%4.1f%%) inst=%-12s %-60s | %s %s\n" % (
                 samp, 100.0 * samp / max(total, 1), inst, " ".join("%s=%d" % (c[6:], v) for v, c in st), ln, text))
     print("wrote", out + "_raw.json", out + "_source_stalls.txt", "lines", len(lines))
