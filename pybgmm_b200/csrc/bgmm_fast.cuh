@@ -42,7 +42,9 @@ constexpr int WIN_PASSES_MAX = 8;
 constexpr int BULK_PASSES_MAX = 4;     // passes of the thread-per-datum evaluator in one window
 constexpr int BULK_MIN_ROWS = TF / 2;   // windows of at least this many data per SM use it: a pass of the
                                         // thread-per-datum evaluator has a long fixed latency (K evaluations in series)
-constexpr int DLOG = 16;              // versions of the dirty log (power of two)
+constexpr int DLOG = 32;              // versions of the dirty log (power of two)
+constexpr int PREP_ZONE = 6;          // rows are prepared from PREP_ZONE windows ahead of the chain (a quiet round can double the window)
+constexpr int PATCH_LAG = 10;         // a complete row that waits is brought up to date once it is this many versions behind
 constexpr int MV_EXTRA = 5;           // mover slot: x[DP], u, log prior, i, uid, drawn component (-1: full step)
 // phase clocks (CTA 0, thread 0; cycles): reported through bgmm_sweep_stats.phase_cycles
 enum { PH_STAGE = 0, PH_HEAD, PH_EVAL, PH_DRAW, PH_UPDATE, PH_SCALARS, PH_WINEVAL, PH_BARRIER, PH_RARE, PH_STEPS, PH_MOVES,
@@ -379,7 +381,7 @@ __device__ __noinline__ double f_eval_lane(const double *__restrict__ col, const
 // f_eval_lane, different summation order (agreement to rounding, ~1e-16).  Whole warp must call.
 // ---------------------------------------------------------------------------------------------
 template <int DP>
-__device__ __noinline__ void f_eval_rows2(const double *__restrict__ rec, const double *__restrict__ x, int ka, int kb,
+__device__ __forceinline__ void f_eval_rows2(const double *__restrict__ rec, const double *__restrict__ x, int ka, int kb,
                                           int k_old, double wref, double *__restrict__ ew,
                                           const double *__restrict__ fmtab) {
     using Ly = Lay<DP>;
@@ -496,7 +498,7 @@ __device__ __forceinline__ double f_finish_weight(const double *__restrict__ sc,
 // ---------------------------------------------------------------------------------------------
 // The lane's (at most NB_MAX) entries are read once into registers: both passes below then run on registers, in the
 // same order as a loop over shared memory would (bit-identical sums; trailing zeros add nothing).
-static __device__ __noinline__ int f_warp_pick(const double *__restrict__ e, int n, double u, double *margin) {
+static __device__ __forceinline__ int f_warp_pick_inl(const double *__restrict__ e, int n, double u, double *margin) {
     const int lane = threadIdx.x & 31;
     const int nb = (n + 31) >> 5;
     const int lo = lane * nb;
@@ -541,6 +543,10 @@ static __device__ __noinline__ int f_warp_pick(const double *__restrict__ e, int
     *margin = mg;
     if (!(s > 0.0) || !(s < INFINITY)) k = -2;
     return k;
+}
+
+static __device__ __noinline__ int f_warp_pick(const double *__restrict__ e, int n, double u, double *margin) {
+    return f_warp_pick_inl(e, n, u, margin);
 }
 
 // log-domain version (crpmm.py:75: exp(w - logsumexp(w))) for weights whose spread overflows the fast scaling:
@@ -1224,7 +1230,7 @@ template <int DP>
 __device__ __forceinline__ void f_row_update(const Params &p, const FSmem<DP> &s, WCache &c, int K, int ver, int k_old,
                                              double wref, const double *xw, double *ew) {
     using Ly = Lay<DP>;
-    const FSh &sh = *s.sh;
+    const FSh &sh = *f_sh<DP>(s, s.sh);
     const int lane = threadIdx.x & 31;
     const int nd = 2 * (ver - c.ver);
     if (nd == 2) {
@@ -1233,14 +1239,17 @@ __device__ __forceinline__ void f_row_update(const Params &p, const FSmem<DP> &s
         int ka = sh.dlog_a[ver & (DLOG - 1)], kb = sh.dlog_b[ver & (DLOG - 1)];
         if (ka >= K) ka = -1;
         if (kb >= K) kb = -1;
-        f_eval_rows2<DP>(s.rec, xw, ka, kb, k_old, wref, ew, p.fmtab);
+        f_eval_rows2<DP>(f_sh<DP>(s, s.rec), xw, ka, kb, k_old, wref, ew, p.fmtab);
         c.ver = ver;
         return;
     }
-    if (lane < nd) {
-        const int v = c.ver + 1 + (lane >> 1);
-        const int k = (lane & 1) ? sh.dlog_b[v & (DLOG - 1)] : sh.dlog_a[v & (DLOG - 1)];
-        if (k >= 0 && k < K) ew[k] = f_eval_lane<DP, Ly::KS>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0, p.fmtab);
+    for (int base = 0; base < nd; base += 32) {   // 16 versions per pass; duplicates write the same value
+        const int t = base + lane;
+        if (t < nd) {
+            const int v = c.ver + 1 + (t >> 1);
+            const int k = (t & 1) ? sh.dlog_b[v & (DLOG - 1)] : sh.dlog_a[v & (DLOG - 1)];
+            if (k >= 0 && k < K) ew[k] = f_eval_lane<DP, Ly::KS>(s.rec + k, xw, k == k_old ? 1 : 0, wref, 0, p.fmtab);
+        }
     }
     __syncwarp();
     c.ver = ver;
@@ -1262,12 +1271,13 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
                               unsigned long long *first_slot, unsigned int round, WCache &c, double &my_margin) {
     using Ly = Lay<DP>;
     constexpr int ST = Ly::KS;
-    const FSh &sh = *s.sh;
+    // shared-memory addressing for the evaluator's own dependent chain (see f_sh); f_eval_lane keeps generic operands
+    const FSh &sh = *f_sh<DP>(s, s.sh);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long G = gridDim.x;
     const long long end = pos + win;
-    double *ew = s.ew + (size_t)warp * Ly::WS;
-    double *xw = s.xw + (size_t)warp * DP;
+    double *ew = f_sh<DP>(s, s.ew) + (size_t)warp * Ly::WS;
+    double *xw = f_sh<DP>(s, s.xw) + (size_t)warp * DP;
     const long long stride = G * NWARP;   // this warp owns the positions congruent to blockIdx.x + G * warp
     const unsigned long long gw = (unsigned long long)(blockIdx.x * NWARP + warp);
     while (c.nj < pos) c.nj += stride;
@@ -1281,13 +1291,22 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
             if (c.stage == 0) {
                 F_WCAT(1);
                 f_load_inputs<DP>(p, c, xw);
-            } else if (c.j - pos < 3 * win) {
-                // evaluate just in time: a row prepared too early would outlive the dirty log.  (Keeping waiting rows
-                // current round by round was measured slower: every warp busy every round slows the critical one.)
+            } else if (c.j - pos < PREP_ZONE * win) {
+                // evaluate ahead of the chain, but not as soon as possible: a waiting row ages with every move.  (Keeping
+                // waiting rows current round by round was measured slower: every warp busy every round slows the
+                // critical one.)  The zone is wide enough that a window which doubles after a quiet round still finds
+                // its rows prepared -- an unprepared row puts nch full evaluations on that round's critical path, and
+                // one in ~15 was unprepared with a zone of 3 windows.
                 if (c.stage >= 2 && !f_row_usable(sh, c, K, ver)) c.stage = 1;
                 if (c.stage - 1 < nch) {
                     F_WCAT(2);
                     f_eval_chunk<DP>(p, s, c, K, ver, xw, ew);
+                } else if (ver - c.ver >= PATCH_LAG && c.uid >= 0) {
+                    // a complete row that keeps waiting: one pass over the components touched since, before it
+                    // outlives the dirty log
+                    F_WCAT(3);
+                    f_row_update<DP>(p, s, c, K, ver, f_sh<DP>(s, s.slot_of_uid)[c.uid], p.log_alpha + c.lp, xw, ew);
+                    c.K = K;
                 }
             }
         }
@@ -1310,8 +1329,8 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
         bool cand = (uid < 0);
         int k_old = -1, drawn = -1;
         if (!cand) {
-            k_old = s.slot_of_uid[uid];
-            if (s.rec[(Ly::SC + F_N) * ST + k_old] == 1.0) cand = true;  // the component would die
+            k_old = f_sh<DP>(s, s.slot_of_uid)[uid];
+            if (f_sh<DP>(s, s.rec)[(Ly::SC + F_N) * ST + k_old] == 1.0) cand = true;  // the component would die
         }
         if (!cand) {
             const double wref = p.log_alpha + c.lp;
@@ -1332,7 +1351,7 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
             int k_new;
             {
                 F_WSUB_BEGIN();
-                k_new = f_warp_pick(ew, K + 1, c.u, &mg);
+                k_new = f_warp_pick_inl(ew, K + 1, c.u, &mg);
                 F_WSUB_END(7);
             }
             if (k_new != k_old) {
