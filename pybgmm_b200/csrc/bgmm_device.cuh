@@ -73,7 +73,7 @@ struct Ctl {
     double gap;         // running estimate of the number of data between two movers
     long long explicit_evals, refreshes;
     long long prof[16];            // phase clocks of CTA 0 (cycles), see bgmm_fast.cuh
-    unsigned long long wsum[8], wcnt[8], wmax[8];  // evaluator unit clocks by category (profile builds)
+    unsigned long long wsum[16], wcnt[16], wmax[16];  // evaluator unit clocks by category (profile builds)
 };
 
 struct Params {
@@ -117,8 +117,10 @@ struct Params {
     double *ntab;             // count table: 8 doubles per count n = 0..N (bgmm_fast.cuh NT_*)
     int KS, Kcap;
     float win_factor;         // window length = win_factor x running gap between movers
+    int near_zone;            // waiting rows within this many windows beyond the current one are kept current (env BGMM_NEAR)
     int tune;                 // developer switches (env BGMM_TUNE): bit 0 = f_step evaluates with one thread per component,
-                              // bit 1 = statistics by load / add / store instead of L2 reductions
+                              // bit 1 = statistics by load / add / store instead of L2 reductions,
+                              // bit 2 = rows about to enter the window are not kept current
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -665,8 +665,9 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         out->explicit_evals = c.explicit_evals; out->refreshes = c.refreshes; out->generic_from = generic_from;
         for (int t = 0; t < 16; ++t) out->phase_cycles[t] = c.prof[t];
         if (getenv("BGMM_WPROF")) {
-            static const char *nm[8] = {"idle", "load", "chunk", "rowup", "stay", "cand", "full", "pick"};
-            for (int t = 0; t < 8; ++t)
+            static const char *nm[16] = {"idle", "load", "chunk", "rowup", "stay", "cand", "full", "pick",
+                                         "w-chunk", "w-patchN", "w-patch2", "w-none", "", "", "", ""};
+            for (int t = 0; t < 16; ++t)
                 if (c.wcnt[t])
                     fprintf(stderr, "  unit %-5s n=%10llu mean=%8.0f max=%8llu cycles\n", nm[t], c.wcnt[t],
                             (double)c.wsum[t] / (double)c.wcnt[t], c.wmax[t]);

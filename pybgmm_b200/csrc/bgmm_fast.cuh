@@ -1301,9 +1301,12 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
                 if (c.stage - 1 < nch) {
                     F_WCAT(2);
                     f_eval_chunk<DP>(p, s, c, K, ver, xw, ew);
-                } else if (ver - c.ver >= PATCH_LAG && c.uid >= 0) {
-                    // a complete row that keeps waiting: one pass over the components touched since, before it
-                    // outlives the dirty log
+                } else if (c.uid >= 0 && c.ver != ver &&
+                           (ver - c.ver >= PATCH_LAG || c.j - end < (long long)(p.tune & 4 ? 0 : p.near_zone) * win)) {
+                    // a complete row that waits is brought up to date (a) before it outlives the dirty log and (b)
+                    // every round once it is within one window of the chain: its first in-window examination then
+                    // costs what a re-examination costs (one two-component update) instead of a pass over everything
+                    // touched since it was prepared -- the slowest first examination is what a round waits for
                     F_WCAT(3);
                     f_row_update<DP>(p, s, c, K, ver, f_sh<DP>(s, s.slot_of_uid)[c.uid], p.log_alpha + c.lp, xw, ew);
                     c.K = K;
@@ -1337,11 +1340,22 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
             if (c.stage >= 2 && !f_row_usable(sh, c, K, ver)) c.stage = 1;
             const bool fresh = (c.stage == 1);
             F_WCAT(fresh ? 6 : 4);
-            while (c.stage - 1 < nch) f_eval_chunk<DP>(p, s, c, K, ver, xw, ew);
+            // (profile builds: 8 = chunks evaluated inside the window, 9 / 10 = row brought up to date over several
+            // versions / over one, 11 = row already current)
+            while (c.stage - 1 < nch) {
+                F_WSUB_BEGIN();
+                f_eval_chunk<DP>(p, s, c, K, ver, xw, ew);
+                F_WSUB_END(8);
+            }
             if (!fresh && c.ver != ver) {
                 F_WSUB_BEGIN();
+                const int nver_ = ver - c.ver;
+                (void)nver_;
                 f_row_update<DP>(p, s, c, K, ver, k_old, wref, xw, ew);
-                F_WSUB_END(3);
+                F_WSUB_END(nver_ > 1 ? 9 : 10);
+            } else {
+                F_WSUB_BEGIN();
+                F_WSUB_END(11);
             }
             if (lane == 0) ew[K] = 1.0;
             __syncwarp();
