@@ -234,6 +234,7 @@ template <int DP> struct FSmem {
     double *mm;       // DP
     int *slot_of_uid, *uid_of_slot, *uid_free;  // K_max each
     unsigned short *rc;  // PP: (a << 8) | b of packed element e
+    double *fm;          // fm::TAB_LEN: the log / exp tables (a global-memory table costs an L1/L2 trip per log and exp)
     FSh *sh;
 };
 
@@ -241,7 +242,7 @@ template <int DP> __host__ __device__ inline size_t fast_smem_bytes(int K_max) {
     using Ly = Lay<DP>;
     size_t d = (size_t)Ly::R * Ly::KS + 2 + 2 * (size_t)Ly::R + (size_t)(NWARP + 1) * Ly::WS + (size_t)NWARP * DP +
                (size_t)SEQ_BATCH * DP + 2 * SEQ_BATCH + SEQ_BATCH /*ib*/ + SEQ_BATCH / 2 /*uidb*/ + 4 * DP + 4 * NT_W +
-               Ly::PP + DP * DP + DP;
+               Ly::PP + DP * DP + DP + fm::TAB_LEN;
     size_t b = d * sizeof(double);
     b += 3 * (size_t)K_max * sizeof(int);
     b += ((size_t)Ly::PP * sizeof(unsigned short) + 15) & ~(size_t)15;
@@ -270,6 +271,7 @@ template <int DP> __device__ inline FSmem<DP> fast_carve(double *base, const Par
     s.A = q; q += Ly::PP;
     s.W = q; q += DP * DP;
     s.mm = q; q += DP;
+    s.fm = q; q += fm::TAB_LEN;
     int *t = (int *)q;
     s.slot_of_uid = t; t += p.K_max;
     s.uid_of_slot = t; t += p.K_max;
@@ -1556,6 +1558,8 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int e = tid; e < fm::TAB_LEN; e += TF) s.fm[e] = __ldg(p_in.fmtab + e);
+    if (tid == 0) p_sh.fmtab = s.fm;   // every later use of p.fmtab reads the shared-memory copy (visible after the barrier below)
     for (int e = tid; e < Ly::PP; e += TF) {
         int a, b;
         decode_row_idx(e, a, b);

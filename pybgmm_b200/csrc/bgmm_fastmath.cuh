@@ -37,7 +37,7 @@ __device__ __forceinline__ double f_log(double x, const double *__restrict__ tab
     const int e = (int)((bits >> 52) & 0x7ff) - 1023;
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);  // [1, 2)
     const int i = (int)((bits >> (52 - 7)) & (LOG_N - 1));
-    const double inv = __ldg(tab + 2 * i), lc = __ldg(tab + 2 * i + 1);
+    const double inv = tab[2 * i], lc = tab[2 * i + 1];   // plain loads: the table may sit in shared memory
     const double r = fma(m, inv, -1.0);                 // |r| <= 2^-8 (+ rounding of inv), exact up to one rounding
     // log1p(r) = r - r^2/2 + r^3/3 - ... ; |r|^9/9 < 2^-75
     double p = fma(r, -1.0 / 8.0, 1.0 / 7.0);
@@ -69,7 +69,7 @@ __device__ __forceinline__ double f_exp(double t, const double *__restrict__ tab
     p = fma(r, p, 1.0 / 6.0);
     p = fma(r, p, 0.5);
     p = fma(r * r, p, r);
-    const double s = __ldg(tab + 2 * LOG_N + (k & (EXP_N - 1)));
+    const double s = tab[2 * LOG_N + (k & (EXP_N - 1))];
     const double v = fma(s, p, s);                       // 2^(j/64) * exp(r)
     const int q = k >> 6;                                // floor division: k = 64 q + j
     // scale by 2^q in two steps (q may be as low as -1075: the result can be subnormal)

@@ -1,9 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for nz in 1 2 3; do
-echo "--- BGMM_NEAR=$nz"
-BGMM_NEAR=$nz timeout 300 python tools/perf_probe.py --sweeps 5 > gpurun_out/probe_n$nz.log 2>&1
-grep -o "^sweep [0-9]*\|'moves': [0-9]*\|'windows': [0-9]*\|'sweep_kernel_ms': [0-9.]*" gpurun_out/probe_n$nz.log | paste - - - - | tail -4
+for wf in 1.0 1.5 3.0; do
+echo "--- BGMM_WIN_FACTOR=$wf"
+BGMM_WIN_FACTOR=$wf timeout 300 python tools/perf_probe.py --sweeps 5 > gpurun_out/probe_w$wf.log 2>&1
+grep -o "^sweep [0-9]*\|'moves': [0-9]*\|'windows': [0-9]*\|'sweep_kernel_ms': [0-9.]*" gpurun_out/probe_w$wf.log | paste - - - - | tail -4
 done
-BGMM_NEAR=2 BGMM_WPROF=1 BGMM_B200_LIB=$PWD/pybgmm_b200/lib/libbgmm_b200_prof.so timeout 300 python tools/perf_probe.py --sweeps 4 > gpurun_out/probe_prof.log 2>&1
-grep "phases\|unit" gpurun_out/probe_prof.log | cut -c1-420 | tail -13
