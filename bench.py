@@ -309,9 +309,15 @@ def run_ours(a):
     K_max = 4 * K_true + 64
     W, K = a.warmup, a.steps
 
-    X, z_true, z0 = gen_data(N, D, K_true, 1 + rank)          # every rank: its own shard / chain
+    # Multi-GPU: a single exact chain does not shard: every rank runs a replica of the workload -- the same
+    # seeded shard and chain, so the per-GPU work is identical at every N (weak scaling of independent processes, no
+    # data-path collective).  --distinct gives every rank its own data and chain instead; the time of a Gibbs sweep
+    # follows the number of data that move, which differs from chain to chain by 3x in the timed sweeps, and the
+    # max-over-ranks time then measures the unluckiest chain rather than the hardware.
+    seed_r = 1 + (rank if a.distinct else 0)
+    X, z_true, z0 = gen_data(N, D, K_true, seed_r)
     m_0, k_0, v_0, S_0 = prior_for(D, cov)
-    orders, unis = step_inputs(N, W + K, power, 1 + rank)
+    orders, unis = step_inputs(N, W + K, power, seed_r)
     chain = _lib.Chain(X, m_0, k_0, v_0, S_0, K_max, covariance_type=cov, device=local_rank)
     stream = torch.cuda.current_stream(dev)
     chain.set_stream(stream.cuda_stream)
@@ -388,8 +394,16 @@ def run_ours(a):
     sync_all()
     t_region1 = time.time()
     clocks = sampler_thread.stop(t_region0, t_region1) if rank == 0 else None
-    ms = reduce_max(e0.elapsed_time(e1))
+    ms_rank = e0.elapsed_time(e1)
+    ms = reduce_max(ms_rank)
     evals = float(sum(st.evals for st in stats))
+    per_rank = None
+    if world > 1:   # every rank's own time and movers in the timed region (what the max is taken over)
+        t = torch.zeros(world, 2, dtype=torch.float64, device=dev)
+        t[rank, 0] = ms_rank
+        t[rank, 1] = float(sum(st.moves for st in stats))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        per_rank = {"ms": [round(v, 3) for v in t[:, 0].tolist()], "moves": [int(v) for v in t[:, 1].tolist()]}
     total_evals = reduce_sum(evals)
     kernel_ms = sum(st.sweep_kernel_ms for st in stats)    # CUDA events around the sweep kernel alone, on its stream
     launches = int(sum(st.launches for st in stats))
@@ -424,7 +438,9 @@ def run_ours(a):
         "data": "synthetic",
         "config": {"workload": "%s: %s D=%d %s N=%d per GPU, K_true=%d, r=%s, rand init K=%d, K_max=%d" % (
             wl, sampler, D, cov, N, K_true, power, K_true, K_max),
-            "chains": "one independent chain/shard per GPU", "l2": "inputs_larger_than_l2 (X %.0f MB + per-step "
+            "chains": ("one independent chain on its own shard per GPU (--distinct)" if a.distinct else
+                       "replicas: every GPU runs the same seeded shard and chain (a single exact chain does not shard)"),
+            "l2": "inputs_larger_than_l2 (X %.0f MB + per-step "
             "order/uniform buffers %.0f MB, never reused; no explicit flush)" % (8e-6 * N * D, 16e-6 * N),
             "K_live_mean": evals / (K * N), "moves_per_sweep": [int(st.moves) for st in stats],
             "K_live": [int(st.K) for st in stats]},
@@ -451,6 +467,7 @@ def run_ours(a):
     }
     if gather_ms is not None:
         line["gather_assignments_ms"] = gather_ms
+        line["per_rank"] = per_rank
     if world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(wl)
     if saved_stdout is not None:
@@ -470,6 +487,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override N per GPU (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--distinct", action="store_true", help="N>1: every rank gets its own data and chain (seed 1+rank)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
