@@ -1,0 +1,34 @@
+"""CPU: the reference arm of bench.py (`--impl reference`: the reference's own CPU path -- oracle/_ref when present, else
+the C port -- on the host cores) prints exactly one JSON line with the contract's keys."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600,
+                       cwd=ROOT)
+    assert r.returncode == 0
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("Gibbs sweeps/sec") and d["steps"] == 1 and d["warmup"] == 1
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["n_gpus"] == 1
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun only rank 0 runs the reference arm; the other ranks print nothing and exit 0."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps",
+                        "1", "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=120,
+                       cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
