@@ -18,7 +18,8 @@
 //     in front of the first datum that does anything else is exactly the sequential chain's decision.
 //     One atomicMin + ONE grid barrier publish that first position (and the warp that holds its inputs);
 //     every CTA then resolves it itself.  Warps keep the inputs of the datum they own across rounds.
-//   * sequential batch: when movers are dense, every CTA walks the scan datum by datum (no barriers).
+//   * sequential batch: when movers are dense, every CTA walks the scan datum by datum (no barriers); one step
+//     puts the whole CTA on the datum (four threads per component, CTA-wide draw: f_step).
 //   * CTA 0 is the only writer of global state: labels (into the sweep's output copy), the bit-exact
 //     statistics (same operation order as the reference: one rounded multiply and one rounded add per
 //     element), counters.  Replicas read mutable global state only between two grid barriers.
