@@ -120,6 +120,7 @@ def main():
         json.dump(cases, fh)
     print("wrote", os.path.join(HERE, "golden.json"), os.path.getsize(os.path.join(HERE, "golden.json")), "bytes")
     adaptive()
+    fixedvar()
 
 
 def adaptive():
@@ -137,6 +138,56 @@ def adaptive():
     with open(os.path.join(HERE, "golden_adap.json"), "w") as fh:
         json.dump({"samplers": A}, fh)
     print("wrote golden_adap.json", len(A), "cases")
+
+
+def fixedvar():
+    """Fixed-variance components (pybgmm/gaussian/gaussian_components_fixedvar.py) and CRPMM / PCRPMM over them
+    (covariance_type="fixed", igmm.py:108-109): leaf values and sampler runs of the reference, for oracle/fixedvar.py."""
+    from pybgmm.gaussian.gaussian_components_fixedvar import GaussianComponentsFixedVar, FixedVarPrior
+    out = {"components": [], "samplers": []}
+    for name, N, D, K_true, seed in (("fixed_3d", 30, 3, 3, 5), ("fixed_1d", 24, 1, 3, 6)):
+        X, _ = gen(N, D, K_true, seed)
+        rng = np.random.RandomState(seed)
+        var, mu_0, var_0 = 0.3 + rng.rand(D), rng.randn(D), 4.0 + 8.0 * rng.rand(D)
+        z = [i % 4 for i in range(N)]
+        z[-1] = -1
+        c = GaussianComponentsFixedVar(X, FixedVarPrior(var, mu_0, var_0), np.array(z), K_max=16)
+        case = {"name": name, "N": N, "D": D, "K_true": K_true, "seed": seed, "var": var.tolist(), "mu_0": mu_0.tolist(),
+                "var_0": var_0.tolist(), "z": z,
+                "log_prior": [float(c.log_prior(i)) for i in range(N)],
+                "log_post_pred": [c.log_post_pred(i).tolist() for i in range(N)],
+                "log_marg_k": [float(c.log_marg_k(k)) for k in range(c.K)]}
+        ops = []
+        for _ in range(40):
+            i = int(rng.randint(N))
+            c.del_item(i)
+            k = int(rng.randint(c.K + 1))
+            c.add_item(i, k)
+            ops.append([i, k])
+        case.update(ops=ops, z_after=c.assignments.tolist(), K_after=int(c.K), counts_after=c.counts[:c.K].tolist(),
+                    num_after=c.mu_N_numerators[:c.K].tolist(), prec_after=c.precision_Ns[:c.K].tolist(),
+                    lpp_after=c.log_prod_precision_preds[:c.K].tolist())
+        out["components"].append(case)
+    for name, cls, N, D, K_true, seed, init, K, n_iter, kw in (
+            ("crpmm_fixed_2d", CRPMM, 120, 2, 3, 3, "rand", 5, 6, {}),
+            ("crpmm_fixed_each_in_own", CRPMM, 40, 2, 3, 4, "each-in-own", 1, 3, {}),
+            ("pcrpmm_fixed_3d_r1.5", PCRPMM, 150, 3, 4, 5, "rand", 6, 6, {"n_power": 1.5, "power_burnin": 0})):
+        X, z_true = gen(N, D, K_true, seed)
+        var, mu_0, var_0 = 0.49 * np.ones(D), np.zeros(D), 16.0 * np.ones(D)
+        model = cls(X, FixedVarPrior(var, mu_0, var_0), 1.0, None, assignments=init, K=K, covariance_type="fixed")
+        z0 = model.components.assignments.copy()
+        rec, _ = model.collapsed_gibbs_sampler(n_iter, z_true, num_saved=0, **kw)
+        c = model.components
+        out["samplers"].append({"name": name, "cls": cls.__name__, "N": N, "D": D, "K_true": K_true, "seed": seed,
+                                "assignments": init, "K_init": K, "n_iter": n_iter, "kwargs": kw,
+                                "var": var.tolist(), "mu_0": mu_0.tolist(), "var_0": var_0.tolist(),
+                                "z0": z0.tolist(), "z": c.assignments.tolist(), "K": int(c.K),
+                                "counts": c.counts[:c.K].tolist(), "log_marg": float(model.log_marg()),
+                                "K_trace": [int(v) for v in rec["components"]],
+                                "log_marg_trace": [float(v) for v in rec["log_marg"]]})
+    with open(os.path.join(HERE, "golden_fixedvar.json"), "w") as fh:
+        json.dump(out, fh)
+    print("wrote golden_fixedvar.json", len(out["components"]), "+", len(out["samplers"]), "cases")
 
 
 if __name__ == "__main__":
