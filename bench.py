@@ -5,14 +5,21 @@
 
 A *step* is one Gibbs sweep (one pass of crpmm.py:57-88 / pcrpmm.py:93-131 over all N data).  Default workload
 = BASELINE.json's target configuration C3: PCRPMM, NIW full covariance, N=1e6, D=16, K_true=100, r=1.5, random scan
-(SURVEY.md 8d), synthetic data from the demos' generator, `rand` initial assignments with K=K_true.  The chain
-starts from that initial state: W warm-up sweeps, then K timed sweeps; no hidden burn-in.
+(SURVEY.md 8d), synthetic data from the demos' generator, `rand` initial assignments with K=K_true.
+
+Protocol ("rand init, one warm-up sweep, time sweeps 2..S"): the W warm-up steps are W sweeps of the
+chain from the rand initial state (the chain's cold sweeps: they warm the device and exercise every engine regime);
+the chain is then put back to the SAME initial state, sweep 0 runs untimed (8d's warm-up sweep), and EXACTLY K sweeps
+-- sweeps 1..K of the chain, cold sweeps included -- are timed.  Nothing converged is hidden in the warm-up: the timed
+region is the run a user pays for.  `regimes` splits the timed sweeps by their share of movers.
 
 Prints ONE JSON line (rank 0).  `value` = whole-job evals/s with the per-step inputs (scan order + uniforms)
-already resident in HBM; `e2e` = the same K sweeps replayed from the same initial state through the host C-ABI
-call (bgmm_sweep) with pinned HOST buffers -> H2D of order+uniforms and D2H of the assignments inside the timed
-region.  Under torchrun (N>1) every rank runs an independent chain on its own shard (weak scaling, no data-path
-collective) and the assignments are all-gathered with NCCL after the timed region.
+already resident in HBM; `e2e` = the same K sweeps replayed from the same state through the host C-ABI call
+(bgmm_sweep) with pinned HOST buffers -> H2D of order+uniforms and D2H of the assignments inside the timed region.
+Under torchrun (N>1) every rank runs its own chain: independent chains (seed 1+rank) on the same data for c2/c3/c4
+(BASELINE.json configs[3]), disjoint 1e6-row shards of one 8e6-row data set for c5 (configs[4]); weak scaling, no
+data-path collective; the assignments are all-gathered with NCCL after the timed region.  `--replicas` makes every
+rank run the same seeded chain instead (identical per-GPU work).
 """
 import argparse
 import json
@@ -39,18 +46,17 @@ METRIC = "Gibbs sweeps/sec (N x K log_post_pred evals)"
 UNIT = "evals/s"
 
 
-def gen_data(N, D, K_true, seed):
-    """examples/crpmm_2d_demo.py:41-55 scaled."""
-    rs = np.random.RandomState(seed)
+def gen_data(N, D, K_true, seed, shard=0, chain_seed=None):
+    """examples/crpmm_2d_demo.py:41-55 scaled.  The component means depend on `seed` alone; the rows of
+    shard `shard` come from their own stream, so shards 0..G-1 are contiguous row blocks of one G*N-row data set.  The
+    initial assignments (igmm.py:86-94 "rand") come from `chain_seed` (default: seed)."""
+    mu = np.random.RandomState(seed).randn(D, K_true) * 4.0
+    rs = np.random.RandomState([seed, 104729 + shard])
     z_true = rs.randint(0, K_true, N)
-    mu = rs.randn(D, K_true) * 4.0
     X = np.ascontiguousarray((mu[:, z_true] + rs.randn(D, N) * 0.7).T)
-    z0 = rs.randint(0, K_true, N).astype(np.int64)
-    for k in range(z0.max()):  # consecutive labels (igmm.py:89-94)
-        while not (z0 == k).any():
-            z0[z0 > k] -= 1
-        if z0.max() == k:
-            break
+    rz = np.random.RandomState([seed if chain_seed is None else chain_seed, 15485863])
+    drawn = rz.randint(0, K_true, N)
+    z0 = np.unique(drawn, return_inverse=True)[1].astype(np.int64)   # consecutive labels (igmm.py:89-94)
     return X, z_true, z0
 
 
@@ -59,12 +65,17 @@ def prior_for(D, cov):
     return np.zeros(D), 0.7 ** 2 / 4.0 ** 2, v_0, 0.7 ** 2 * v_0 * (np.eye(D) if cov == "full" else np.ones(D))
 
 
+def step_input(N, s, power, seed):
+    """Scan order (pcrpmm.py:89) and uniforms (utils.py:15) of sweep `s` of chain `seed`, generated on the host like
+    the reference does; a function of (seed, s) only, so sweep s is the same whatever --steps / --warmup are."""
+    rs = np.random.RandomState([seed, 7919, s])
+    order = rs.permutation(N).astype(np.int64) if power > 1 else None
+    return order, rs.random_sample(N)
+
+
 def step_inputs(N, n_steps, power, seed):
-    """Per-step scan order (pcrpmm.py:89) and uniforms (utils.py:15), generated on the host like the reference."""
-    rs = np.random.RandomState(seed + 7919)
-    orders = [rs.permutation(N).astype(np.int64) if power > 1 else None for _ in range(n_steps)]
-    unis = [rs.random_sample(N) for _ in range(n_steps)]
-    return orders, unis
+    pairs = [step_input(N, s, power, seed) for s in range(n_steps)]
+    return [o for o, _ in pairs], [u for _, u in pairs]
 
 
 class ClockSampler(threading.Thread):
@@ -121,58 +132,74 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
-    """DRAM bytes per launch of the sweep kernel from the committed ncu --set full capture, if any."""
+def ncu_profile(workload, regime):
+    """Per-launch figures of the sweep kernel from the committed `ncu --set full` capture of `regime` (cold / window /
+    converged), profiles/ncu_traffic.json: DRAM bytes, FP64 pipe %, issue-active %.  None when no capture exists."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            return json.load(fh).get(workload)
+            return json.load(fh).get(workload, {}).get(regime)
     except Exception:
         return None
+
+
+def regime_of(moves, N):
+    """cold: >= 10 % of the data move in the sweep (sequential regime); window: some move; converged: (almost) none."""
+    if moves >= 0.1 * N:
+        return "cold"
+    return "window" if moves > 1e-5 * N else "converged"
 
 
 # ------------------------------------------------------------------------------------------------------------
 # CPU arms: the reference's own implementation (oracle/_ref, mechanically shimmed Python) or the C oracle port
 # ------------------------------------------------------------------------------------------------------------
 def _cpu_chain(kind, sampler, X, z0, cov, K_max, power, seed):
-    """Returns step() -> evals of one sweep on the CPU."""
+    """Returns (step, reset): step() runs the next sweep of the chain on the CPU and returns its evals; reset() puts
+    the chain back to the initial state (sweep index 0).  Same per-sweep inputs protocol as the GPU arm: sweep 0 is
+    plain CRP (pcrpmm.py:105: the power applies once i_iter > power_burnin = 0), the scan is random from sweep 0."""
     import random
     m_0, k_0, v_0, S_0 = prior_for(X.shape[1], cov)
-    random.seed(seed)
-    np.random.seed(seed)
+    state = {"i": 0, "model": None}
+    N = X.shape[0]
     if kind == "reference":
         from oracle.make_ref import import_ref
         NIW, CRPMM, PCRPMM, _, _ = import_ref()
         cls = CRPMM if sampler == "CRPMM" else PCRPMM
-        model = cls(X, NIW(m_0, k_0, v_0, S_0), 1.0, None, assignments=z0.tolist(), K_max=K_max, covariance_type=cov)
-        state = {"i": 0}
+
+        def reset():
+            random.seed(seed)
+            np.random.seed(seed)
+            model = cls(X, NIW(m_0, k_0, v_0, S_0), 1.0, None, assignments=z0.tolist(), K_max=K_max, covariance_type=cov)
+            # the reference's update_record_dict computes O(K_true K N) Python metrics; the sweep alone is timed
+            model.update_record_dict = lambda rec, i, z, t: rec
+            state["model"], state["i"] = model, 0
 
         def step():
-            # one sweep through the reference's own public method, continuing the chain: the power schedule is
-            # `i_iter > power_burnin` (pcrpmm.py:105), so power_burnin=-1 keeps the power on for a 1-sweep call
+            model = state["model"]
             K_before = model.components.K
             if sampler == "CRPMM":
                 model.collapsed_gibbs_sampler(1, None, num_saved=0)
-            else:
+            else:  # one sweep through the reference's own public method, continuing the chain
                 model.collapsed_gibbs_sampler(1, None, n_power=power, power_burnin=(-1 if state["i"] > 0 else 0),
                                               num_saved=0)
             state["i"] += 1
-            return X.shape[0] * 0.5 * (K_before + model.components.K)
-        # the reference's update_record_dict needs labels for its metrics; give it a no-op to time the sweep only
-        model.update_record_dict = lambda rec, i, z, t: rec
-        return step
+            return N * 0.5 * (K_before + model.components.K)
+        reset()
+        return step, reset
     from oracle import oracle as O
-    orc = O.Oracle(X, m_0, k_0, v_0, S_0, K_max=K_max, covariance_type=cov)
-    orc.set_assignments(z0)
-    tab = O.logcount_table(X.shape[0], power) if power > 1 else None
-    state = {"i": 0}
-    rs = np.random.RandomState(seed)
+    tab = O.logcount_table(N, power) if power > 1 else None
+
+    def reset():
+        orc = O.Oracle(X, m_0, k_0, v_0, S_0, K_max=K_max, covariance_type=cov)
+        orc.set_assignments(z0)
+        state["model"], state["i"] = orc, 0
 
     def step():
-        order = rs.permutation(X.shape[0]) if power > 1 else None
-        st = orc.sweep(rs.random_sample(X.shape[0]), 1.0, order=order, logcount_tab=tab if state["i"] > 0 else None)
+        order, u = step_input(N, state["i"], power, seed)
+        st = state["model"].sweep(u, 1.0, order=order, logcount_tab=tab if state["i"] > 0 else None)
         state["i"] += 1
         return st.evals
-    return step
+    reset()
+    return step, reset
 
 
 def cpu_kind():
@@ -184,32 +211,41 @@ def cpu_kind():
         return "port"
 
 
+N_CPU = 20000   # the CPU arm runs the first N_cpu = 2e4 rows (the reference at full N is ~30 min/sweep)
+
+
+def cpu_rows(kind, wl, rows=0):
+    if rows:
+        return rows
+    D = WORKLOADS[wl][2]
+    if kind == "reference":
+        return {64: 4000}.get(D, N_CPU)     # D = 64: ~1e3 data/s per core and an N x D x D outer-product cache
+    return {64: 20000}.get(D, 10 * N_CPU)   # the C port is ~10x the reference per core
+
+
 def _cpu_worker(args):
-    kind, wl, n_rows, seed, n_warm, n_steps, conn = args
+    kind, wl, n_rows, seed, conn = args
     sampler, N, D, K_true, power, cov = WORKLOADS[wl]
-    X, _, z0 = gen_data(n_rows, D, K_true, seed)
-    step = _cpu_chain(kind, sampler, X, z0, cov, 4 * K_true + 64, power, seed)
+    X, _, z0 = gen_data(n_rows, D, K_true, 1, chain_seed=seed)
+    step, reset = _cpu_chain(kind, sampler, X, z0, cov, 4 * K_true + 64, power, seed)
     conn.send("ready")
     while True:
         msg = conn.recv()
         if msg == "stop":
             break
+        if msg == "reset":
+            reset()
+            conn.send("ok")
+            continue
         t = time.perf_counter()
         ev = step()
         conn.send((ev, time.perf_counter() - t))
 
 
-def cpu_rows(kind, wl):
-    # bounded sample: the reference is ~5e2..3e3 data/s per core, the C port ~2e4 data/s
-    D = WORKLOADS[wl][2]
-    if kind == "reference":
-        return {2: 6000, 8: 4000, 16: 2500, 64: 600}.get(D, 2500)
-    return {2: 200000, 8: 60000, 16: 30000, 64: 3000}.get(D, 30000)
-
-
 def run_reference_arm(a):
     """bench.py --impl reference: the reference's CPU path on all host cores (independent seeded chains, one per
-    process -- the reference itself is single threaded), same workload / metric / unit, bounded row sample."""
+    process -- the reference itself is single threaded), same workload / metric / unit / protocol (W warm-up sweeps
+    from the rand initial state, back to the initial state, sweep 0 untimed, K timed sweeps), bounded row sample."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -218,12 +254,12 @@ def run_reference_arm(a):
     wl = a.workload
     sampler, N, D, K_true, power, cov = WORKLOADS[wl]
     cores = max(1, min(os.cpu_count() or 1, 64))
-    n_rows = cpu_rows(kind, wl)
+    n_rows = cpu_rows(kind, wl, a.rows)
     ctx = mp.get_context("spawn")
     pipes, procs = [], []
     for w in range(cores):
         pa, pb = ctx.Pipe()
-        p = ctx.Process(target=_cpu_worker, args=((kind, wl, n_rows, 1 + w, a.warmup, a.steps, pb),), daemon=True)
+        p = ctx.Process(target=_cpu_worker, args=((kind, wl, n_rows, 1 + w, pb),), daemon=True)
         p.start()
         pipes.append(pa); procs.append(p)
     for pa in pipes:
@@ -236,6 +272,11 @@ def run_reference_arm(a):
         return sum(r[0] for r in res), max(r[1] for r in res)
     for _ in range(a.warmup):
         one_step()
+    for pa in pipes:
+        pa.send("reset")
+    for pa in pipes:
+        assert pa.recv() == "ok"
+    one_step()      # sweep 0 of the chain, untimed
     evals, t0 = 0.0, time.perf_counter()
     for _ in range(a.steps):
         ev, _ = one_step()
@@ -244,14 +285,15 @@ def run_reference_arm(a):
     for pa in pipes:
         pa.send("stop")
     value = evals / wall
-    sample = "%d independent seeded chains (one per core) x first-%d-row sample of %s, %s sampler, K_true=%d" % (
-        cores, n_rows, wl, sampler, K_true)
+    sample = ("%d independent seeded chains (one per core) x first-%d-row sample of %s, %s sampler, K_true=%d; timed: "
+              "sweeps 1..%d from the rand initial state" % (cores, n_rows, wl, sampler, K_true, a.steps))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %s D=%d %s K_true=%d r=%s (CPU: rows=%d per chain)" % (
-            wl, sampler, D, cov, K_true, power, n_rows)},
+            wl, sampler, D, cov, K_true, power, n_rows),
+            "protocol": "W warm-up sweeps from the rand initial state, reset, sweep 0 untimed, sweeps 1..K timed"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sweeps_per_s_per_chain": a.steps / wall,
@@ -260,21 +302,22 @@ def run_reference_arm(a):
 
 
 def cpu_baseline_leg(wl, budget_s=25.0):
-    """1-core CPU baseline timed inside the default run (rank 0, N=1): the reference if importable, else the port."""
+    """1-core CPU baseline timed inside the default run (rank 0, N=1): the reference if importable, else the port.
+    Same protocol on a bounded sample: sweep 0 untimed, then sweeps 1.. until the budget is spent (at most 5)."""
     kind = cpu_kind()
     sampler, N, D, K_true, power, cov = WORKLOADS[wl]
     n_rows = cpu_rows(kind, wl)
     X, _, z0 = gen_data(n_rows, D, K_true, 1)
-    step = _cpu_chain(kind, sampler, X, z0, cov, 4 * K_true + 64, power, 1)
-    step()  # warm-up sweep
+    step, _ = _cpu_chain(kind, sampler, X, z0, cov, 4 * K_true + 64, power, 1)
+    step()  # sweep 0, untimed
     evals, t0, n = 0.0, time.perf_counter(), 0
-    while n < 1 or (time.perf_counter() - t0 < budget_s * 0.5 and n < 5):
+    while n < 1 or (time.perf_counter() - t0 < budget_s * 0.6 and n < 5):
         evals += step()
         n += 1
     wall = time.perf_counter() - t0
     return {"value": evals / wall, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "first %d rows of %s, %d timed sweep(s) after 1 warm-up, single process (the reference is "
-                      "single threaded)" % (n_rows, wl, n)}
+            "sample": "first %d rows of %s, sweeps 1..%d timed after sweep 0 from the rand initial state, single "
+                      "process (the reference is single threaded)" % (n_rows, wl, n)}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -288,15 +331,12 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     saved_stdout = None
     if world > 1:
-        # stdout carries the ONE JSON line: anything the collectives library prints there at communicator set-up (NCCL's
-        # version banner) goes to stderr instead -- file descriptor 1 is pointed at stderr until the line is printed
+        # stdout carries the ONE JSON line: anything a library prints there at communicator set-up goes to stderr
+        # instead -- file descriptor 1 is pointed at stderr until the line is printed (NCCL_DEBUG is left alone)
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on stdout when NCCL_DEBUG is VERSION/INFO; stdout carries the JSON line only
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if not torch.cuda.is_available() or _lib.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
@@ -309,15 +349,18 @@ def run_ours(a):
     K_max = 4 * K_true + 64
     W, K = a.warmup, a.steps
 
-    # Multi-GPU: a single exact chain does not shard: every rank runs a replica of the workload -- the same
-    # seeded shard and chain, so the per-GPU work is identical at every N (weak scaling of independent processes, no
-    # data-path collective).  --distinct gives every rank its own data and chain instead; the time of a Gibbs sweep
-    # follows the number of data that move, which differs from chain to chain by 3x in the timed sweeps, and the
-    # max-over-ranks time then measures the unluckiest chain rather than the hardware.
-    seed_r = 1 + (rank if a.distinct else 0)
-    X, z_true, z0 = gen_data(N, D, K_true, seed_r)
+    # Multi-GPU: a single exact chain does not shard; the two fan-outs BASELINE.json names are independent
+    # chains on the same data (configs[3]: seeds 1..G) and disjoint contiguous shards of one data set (configs[4]).
+    if a.replicas or world == 1:
+        shard, chain_seed, fan = 0, 1, ("replicas: every GPU runs the same seeded chain" if world > 1 else "one chain")
+    elif wl == "c5":
+        shard, chain_seed, fan = rank, 1 + rank, "disjoint shards: rank g owns rows [g N, (g+1) N) of one %d-row data set" % (world * N)
+    else:
+        shard, chain_seed, fan = 0, 1 + rank, "independent chains: rank g runs chain seed 1+g on the same data"
+    X, z_true, z0 = gen_data(N, D, K_true, 1, shard=shard, chain_seed=chain_seed)
     m_0, k_0, v_0, S_0 = prior_for(D, cov)
-    orders, unis = step_inputs(N, W + K, power, seed_r)
+    n_sw = max(W, K + 1)
+    orders, unis = step_inputs(N, n_sw, power, chain_seed)
     chain = _lib.Chain(X, m_0, k_0, v_0, S_0, K_max, covariance_type=cov, device=local_rank)
     stream = torch.cuda.current_stream(dev)
     chain.set_stream(stream.cuda_stream)
@@ -328,68 +371,41 @@ def run_ours(a):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def reduce_max(x):
+    def reduce(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def reduce_max(x):
+        return reduce(x, dist.ReduceOp.MAX if world > 1 else None)
+
     def reduce_sum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce(x, dist.ReduceOp.SUM if world > 1 else None)
 
     def pw(s):  # pcrpmm.py:105: the power applies once i_iter > power_burnin (= 0)
         return power if (power > 1 and s > 0) else 1.0
 
-    # ---------------- e2e arm: host buffers through the C-ABI call -------------------------------------------
-    pin_o = [torch.from_numpy(o).pin_memory() if o is not None else None for o in orders]
-    pin_u = [torch.from_numpy(u).pin_memory() for u in unis]
-    z_host = torch.empty(N, dtype=torch.int64).pin_memory()
-    z_host_np = z_host.numpy()
-    chain.set_assignments(z0)
-    for s in range(W):
-        chain.sweep(1.0, pw(s), None if pin_o[s] is None else pin_o[s].numpy(), pin_u[s].numpy())
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall = time.perf_counter()
-    e0.record(stream)
-    e2e_evals = 0
-    for s in range(W, W + K):
-        st = chain.sweep(1.0, pw(s), None if pin_o[s] is None else pin_o[s].numpy(), pin_u[s].numpy())
-        e2e_evals += st.evals
-        # device -> host read of the step's result: the relabelled assignments
-        _lib._check(_lib.lib().bgmm_get_state(chain._h, _lib._ip(z_host_np), None, None, None, None, None, None))
-    e1.record(stream)
-    sync_all()
-    e2e_ms = reduce_max(max(e0.elapsed_time(e1), 1e3 * 0))
-    e2e_wall_ms = reduce_max(1e3 * (time.perf_counter() - t_wall))
-    e2e_ms = max(e2e_ms, e2e_wall_ms)  # host work between launches counts end to end
-    e2e_total_evals = reduce_sum(float(e2e_evals))
-    z_e2e = z_host_np.copy()
-    h2d = (8 * N if power > 1 else 0) + 8 * N
-    d2h = 8 * N
-
-    # ---------------- device-resident arm: same initial state, same inputs, already in HBM -------------------
+    # ---------------- device-resident arm: inputs already in HBM -------------------------------------------------
     d_o = [torch.from_numpy(o).to(dev) if o is not None else None for o in orders]
     d_u = [torch.from_numpy(u).to(dev) for u in unis]
-    chain.set_assignments(z0)
+
+    def dev_sweep(s):
+        return chain.sweep_dev(1.0, pw(s), 0 if d_o[s] is None else d_o[s].data_ptr(), d_u[s].data_ptr())
     sampler_thread = ClockSampler(local_rank)
     if rank == 0:
         sampler_thread.start()
-    warm = []
-    for s in range(W):
-        warm.append(chain.sweep_dev(1.0, pw(s), 0 if d_o[s] is None else d_o[s].data_ptr(), d_u[s].data_ptr()))
+    chain.set_assignments(z0)
+    warm = [dev_sweep(s) for s in range(W)]          # W warm-up steps: the chain's own cold sweeps
+    chain.set_assignments(z0)                        # back to the initial state
+    sweep0 = dev_sweep(0)                            # one untimed sweep, then time sweeps 1..K
     sync_all()
     sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_region0 = time.time()
     e0.record(stream)
-    stats = []
-    for s in range(W, W + K):
-        stats.append(chain.sweep_dev(1.0, pw(s), 0 if d_o[s] is None else d_o[s].data_ptr(), d_u[s].data_ptr()))
+    stats = [dev_sweep(s) for s in range(1, K + 1)]
     e1.record(stream)
     sync_all()
     t_region1 = time.time()
@@ -397,29 +413,67 @@ def run_ours(a):
     ms_rank = e0.elapsed_time(e1)
     ms = reduce_max(ms_rank)
     evals = float(sum(st.evals for st in stats))
+    total_evals = reduce_sum(evals)
+    rate_sum = reduce_sum(evals / (ms_rank * 1e-3))
     per_rank = None
     if world > 1:   # every rank's own time and movers in the timed region (what the max is taken over)
-        t = torch.zeros(world, 2, dtype=torch.float64, device=dev)
+        t = torch.zeros(world, 3, dtype=torch.float64, device=dev)
         t[rank, 0] = ms_rank
         t[rank, 1] = float(sum(st.moves for st in stats))
+        t[rank, 2] = evals
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        per_rank = {"ms": [round(v, 3) for v in t[:, 0].tolist()], "moves": [int(v) for v in t[:, 1].tolist()]}
-    total_evals = reduce_sum(evals)
+        per_rank = {"ms": [round(v, 3) for v in t[:, 0].tolist()], "moves": [int(v) for v in t[:, 1].tolist()],
+                    "evals_per_s": [e / (m * 1e-3) for m, e in zip(t[:, 0].tolist(), t[:, 2].tolist())]}
     kernel_ms = sum(st.sweep_kernel_ms for st in stats)    # CUDA events around the sweep kernel alone, on its stream
     launches = int(sum(st.launches for st in stats))
-    same = bool((chain.assignments() == z_e2e).all())      # both arms walked the same chain
+    z_value_arm = chain.assignments()
 
-    # gather of per-rank assignments at the end (NCCL over NVLink), outside the timed steps
+    # ---------------- e2e arm: the same sweeps from the same state, host buffers through the C-ABI call ---------
+    pin_o = [torch.from_numpy(o).pin_memory() if o is not None else None for o in orders]
+    pin_u = [torch.from_numpy(u).pin_memory() for u in unis]
+    z_host = torch.empty(N, dtype=torch.int64).pin_memory()
+    z_host_np = z_host.numpy()
+
+    def host_sweep(s):
+        return chain.sweep(1.0, pw(s), None if pin_o[s] is None else pin_o[s].numpy(), pin_u[s].numpy())
+    chain.set_assignments(z0)
+    host_sweep(0)                                    # sweep 0 untimed (also the host path's warm-up)
+    sync_all()
+    t_wall = time.perf_counter()
+    e0.record(stream)
+    e2e_evals = 0
+    for s in range(1, K + 1):
+        st = host_sweep(s)
+        e2e_evals += st.evals
+        # device -> host read of the step's result: the relabelled assignments
+        _lib._check(_lib.lib().bgmm_get_state(chain._h, _lib._ip(z_host_np), None, None, None, None, None, None))
+    e1.record(stream)
+    sync_all()
+    e2e_ms = max(reduce_max(e0.elapsed_time(e1)), reduce_max(1e3 * (time.perf_counter() - t_wall)))
+    e2e_total_evals = reduce_sum(float(e2e_evals))
+    same = bool((z_value_arm == z_host_np).all())          # both arms walked the same chain
+    h2d = (8 * N if power > 1 else 0) + 8 * N
+    d2h = 8 * N
+
+    # gather of per-rank assignments at the end (NCCL over NVLink), outside the timed steps; the first call carries
+    # NCCL's lazy set-up of the all_gather channels, the second is the steady-state cost
     gather_ms = None
     if world > 1:
         zt = fanout.chain_assignments_tensor(chain, dev)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sync_all()
-        g0.record()
-        outs, ks = fanout.gather_assignments(zt, chain.K)
-        g1.record()
-        sync_all()
-        gather_ms = reduce_max(g0.elapsed_time(g1))
+        gather_ms = []
+        for _ in range(2):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sync_all()
+            g0.record()
+            outs, ks = fanout.gather_assignments(zt, chain.K)
+            g1.record()
+            sync_all()
+            gather_ms.append(reduce_max(g0.elapsed_time(g1)))
+
+    # ---------------- optional: many independent chains on this GPU (bgmm_sweep_many) ---------------------------
+    multi = None
+    if a.chains > 1 and world == 1:
+        multi = run_multi_chain(a, _lib, torch, dev, X, z0, (m_0, k_0, v_0, S_0), K_max, cov, power, N, K)
 
     if rank != 0:
         if world > 1:
@@ -432,42 +486,64 @@ def run_ours(a):
     alg_bytes = evals * b_eval + K * N * b_datum                            # this rank, K launches
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     flops_eval = (D * D + 3 * D + 30) if cov == "full" else (8 * D + 30)    # ~fp64 FMAs*2 per eval, DESIGN.md
+    # regimes of the timed sweeps (by share of movers) and the one that dominates the timed region's time
+    regimes = {}
+    for st in stats:
+        r = regimes.setdefault(regime_of(st.moves, N), {"sweeps": 0, "ms": 0.0, "evals": 0.0, "moves": 0})
+        r["sweeps"] += 1; r["ms"] += st.sweep_kernel_ms; r["evals"] += st.evals; r["moves"] += int(st.moves)
+    for r in regimes.values():
+        r["evals_per_s"] = r["evals"] / (r["ms"] * 1e-3) if r["ms"] > 0 else None
+        r["us_per_mover"] = 1e3 * r["ms"] / r["moves"] if r["moves"] else None
+    dominant = max(regimes, key=lambda k: regimes[k]["ms"])
+    prof = ncu_profile(wl, dominant) or {}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "%s: %s D=%d %s N=%d per GPU, K_true=%d, r=%s, rand init K=%d, K_max=%d" % (
             wl, sampler, D, cov, N, K_true, power, K_true, K_max),
-            "chains": ("one independent chain on its own shard per GPU (--distinct)" if a.distinct else
-                       "replicas: every GPU runs the same seeded shard and chain (a single exact chain does not shard)"),
-            "l2": "inputs_larger_than_l2 (X %.0f MB + per-step "
-            "order/uniform buffers %.0f MB, never reused; no explicit flush)" % (8e-6 * N * D, 16e-6 * N),
+            "protocol": "W warm-up sweeps from the rand initial state, chain put back to that state, sweep 0 untimed, "
+                        "sweeps 1..K timed (SURVEY.md 8d): the cold sweeps are inside the timed region",
+            "chains": fan,
+            "l2": "inputs_larger_than_l2 (X %.0f MB + per-step order/uniform buffers %.0f MB, never reused; no "
+                  "explicit flush)" % (8e-6 * N * D, 16e-6 * N),
             "K_live_mean": evals / (K * N), "moves_per_sweep": [int(st.moves) for st in stats],
-            "K_live": [int(st.K) for st in stats]},
+            "ms_per_sweep": [round(st.device_ms, 3) for st in stats], "K_live": [int(st.K) for st in stats]},
         "sweeps_per_s": world * K / (ms * 1e-3),
+        "sum_of_rank_rates": rate_sum,
         "e2e": {"value": e2e_total_evals / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K, "same_chain_as_value_arm": same},
         "gpu_launches": launches,
         "clocks": clocks,
+        "regimes": regimes,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(wl), "peak_source": peak_src, "kernel": "k_fast_sweep<16> (one launch = one sweep)" if (cov == "full" and D <= 16) else "k_sweep",
+                     "traffic": prof.get("dram_bytes"), "traffic_regime": dominant if prof else None,
+                     "peak_source": peak_src,
+                     "kernel": "k_fast_sweep<%d> (one launch = one sweep)" % D if (cov == "full" and D <= 16) else "k_sweep",
                      "algorithmic_bytes_per_eval": b_eval, "algorithmic_bytes_per_datum": b_datum,
                      "kernel_ms_per_launch": kernel_ms / K,
+                     "true_bound": "latency of the sequential dependency: every datum that moves is one serial step "
+                                   "(cold regime) or one window round (window regime); HBM and the FP64 pipe are "
+                                   "both far from saturated",
                      "fp64_tflops": evals * 2 * flops_eval / (kernel_ms * 1e-3) / 1e12,
-                     "note": "algorithmic bytes per SURVEY.md 8(d): one sufficient-statistic record per eval; the "
-                             "records live in every CTA's shared memory and are reused across data, so DRAM "
-                             "traffic is far below this figure and the sweep is bound by the sequential "
-                             "dependency (one window round per mover), not by HBM (see DESIGN.md 4)"},
-        "cold_chain": {"note": "the %d untimed warm-up sweeps from the rand initial state, device-resident arm" % W,
-                       "ms": [round(st.device_ms, 3) for st in warm], "moves": [int(st.moves) for st in warm],
-                       "K_live": [int(st.K) for st in warm],
-                       "evals_per_s": [st.evals / (st.device_ms * 1e-3) for st in warm]},
+                     "ncu": prof or None,
+                     "note": "secondary figure: ALGORITHMIC bytes per SURVEY.md 8(d) (one sufficient-statistic record "
+                             "per eval) over the timed kernel time; the records live in shared memory / registers "
+                             "and are reused across data, so DRAM traffic (`traffic`, ncu capture of the regime that "
+                             "dominates the timed region) is far below it"},
+        "warmup_chain": {"note": "the %d untimed warm-up sweeps from the rand initial state" % W,
+                         "ms": [round(st.device_ms, 3) for st in warm], "moves": [int(st.moves) for st in warm]},
+        "sweep0": {"ms": round(sweep0.device_ms, 3), "moves": int(sweep0.moves), "K_live": int(sweep0.K)},
         "engine": {"windows": [int(st.windows) for st in stats], "seq_data": [int(st.seq_data) for st in stats],
-                   "wasted": [int(st.wasted) for st in stats], "min_margin": min(st.min_margin for st in stats)},
+                   "fast_steps": [int(st.fast_steps) for st in stats],
+                   "wasted": [int(st.wasted) for st in stats], "min_margin": min(st.min_margin for st in stats),
+                   "guard_hits": int(sum(st.guard_hits for st in stats) + sweep0.guard_hits)},
     }
     if gather_ms is not None:
-        line["gather_assignments_ms"] = gather_ms
+        line["gather_assignments_ms"] = {"first_call": gather_ms[0], "steady": gather_ms[1]}
         line["per_rank"] = per_rank
+    if multi is not None:
+        line["multi_chain"] = multi
     if world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(wl)
     if saved_stdout is not None:
@@ -478,6 +554,47 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_multi_chain(a, _lib, torch, dev, X, z0_first, prior, K_max, cov, power, N, K):
+    """`--chains M`: M independent chains (seeds 1..M) on the same data resident on ONE GPU, one CTA each, all advanced
+    by one kernel launch per sweep (bgmm_sweep_many).  Same protocol: sweep 0 untimed, sweeps 1..K timed."""
+    M = a.chains
+    m_0, k_0, v_0, S_0 = prior
+    D = X.shape[1]
+    K_true = WORKLOADS[a.workload][3]
+    first = _lib.Chain(X, m_0, k_0, v_0, S_0, K_max, covariance_type=cov, device=dev.index)
+    chains = [first] + [first.fork() for _ in range(M - 1)]
+    stream = torch.cuda.current_stream(dev)
+    for c in chains:
+        c.set_stream(stream.cuda_stream)
+    for m, c in enumerate(chains):
+        c.set_assignments(gen_data(N, D, K_true, 1, chain_seed=1 + m)[2] if m else z0_first)
+    rs = np.random.RandomState(4242)
+
+    def inputs():
+        o = torch.stack([torch.from_numpy(rs.permutation(N).astype(np.int64)) for _ in range(M)]).to(dev) if power > 1 else None
+        u = torch.from_numpy(rs.random_sample((M, N))).to(dev)
+        return o, u
+    group = _lib.ChainGroup(chains)
+    o, u = inputs()
+    group.sweep_dev(1.0, 1.0, o, u)                  # sweep 0 untimed
+    torch.cuda.synchronize(dev)
+    ins = [inputs() for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    evals, moves = 0, []
+    for s in range(K):
+        sts = group.sweep_dev(1.0, power if power > 1 else 1.0, ins[s][0], ins[s][1])
+        evals += sum(st.evals for st in sts)
+        moves.append(int(sum(st.moves for st in sts)))
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    return {"chains": M, "value": evals / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
+            "moves_per_sweep_all_chains": moves,
+            "note": "%d independent exact chains on one GPU (one CTA per chain, register-resident sequential engine), "
+                    "one launch per sweep; aggregate evals/s over sweeps 1..%d from rand initial states" % (M, K)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -485,11 +602,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--rows", type=int, default=0, help="override N per GPU (debug)")
+    ap.add_argument("--rows", type=int, default=0, help="override N per GPU / rows per CPU chain (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--distinct", action="store_true", help="N>1: every rank gets its own data and chain (seed 1+rank)")
+    ap.add_argument("--replicas", action="store_true", help="N>1: every rank runs the same seeded chain")
+    ap.add_argument("--chains", type=int, default=0, help="also time this many independent chains on one GPU")
     a = ap.parse_args()
-    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
         run_reference_arm(a)
     else:

@@ -33,6 +33,7 @@ extern "C" {
 #define BGMM_EKMAX (-3)    /* a birth would exceed K_max                     (reference: IndexError, gaussian_components.py:161) */
 #define BGMM_ENUMERIC (-4) /* covariance not positive definite / NaN         (reference: LinAlgError or NaN weights) */
 #define BGMM_ENOMEM (-5)
+#define BGMM_EWATCHDOG (-6) /* a device spin loop timed out (replicas of the sweep kernel stopped agreeing)          */
 
 #define BGMM_COV_FULL 0 /* NIW, full covariance      -- pybgmm/gaussian/gaussian_components.py      */
 #define BGMM_COV_DIAG 1 /* product of NIX, diagonal  -- pybgmm/gaussian/gaussian_components_diag.py */
@@ -57,6 +58,8 @@ typedef struct {
     int64_t phase_cycles[16]; /* SM cycles CTA 0 spent per engine phase in the last sweep (engine diagnostic)   */
     int64_t launches;         /* kernels launched by this call                                                  */
     double sweep_kernel_ms;   /* CUDA-event time of the sweep kernel alone (device_ms also covers record set-up) */
+    int64_t guard_hits;       /* draws whose margin was below the guard and were redone on the exact path (bgmm_set_guard) */
+    int64_t fast_steps;       /* data resolved by the register-resident sequential step (engine diagnostic)             */
 } bgmm_sweep_stats;
 
 const char *bgmm_version(void);
@@ -155,6 +158,19 @@ int bgmm_del_item(bgmm_t *h, int64_t i);
 /* replaces: restore_component_from_stats(k, ...) (gaussian_components.py:144-152): overwrite the sufficient statistics
  * of live component k (m_num: D, S_part: D*D full | D diag, count) -- logdet/inv are re-derived from them. */
 int bgmm_set_component_stats(bgmm_t *h, int32_t k, const double *m_num, const double *S_part, int64_t count);
+
+/* replaces: the caller-side `components.assignments[i] = k_old` that completes the reference's restore path
+ * (crpmm.py:84-85): rewrite the label of datum i (k = -1: unassigned) without touching any statistic. */
+int bgmm_set_label(bgmm_t *h, int64_t i, int32_t k);
+/* Resume from a saved state (SURVEY.md 8b bgmm_set_state; the reference's in-memory snapshots are copy.deepcopy of
+ * the components, cscrpmm.py:173): bgmm_set_assignments(z), then -- when m_num / S_part (K x D, K x D*D | K x D) are
+ * given -- the exact bits of the saved statistics per component (bgmm_set_component_stats). */
+int bgmm_set_state(bgmm_t *h, const int64_t *z, int32_t K, const double *m_num, const double *S_part);
+/* Margin guard of the draw (no counterpart in the reference): a draw whose uniform is closer than `guard`
+ * (probability units) to a boundary of the drawn interval is redone on the exact path (records rebuilt from the
+ * statistics, libm log / exp, sequential-subtract draw of utils.py:15-20).  Default 1e-9 (env BGMM_GUARD at create);
+ * 0 disables.  bgmm_sweep_stats.guard_hits counts the redone draws. */
+int bgmm_set_guard(bgmm_t *h, double guard);
 
 /*
  * replaces: the stream of random.random() calls made by utils.draw (utils/utils.py:15).  `state` is the 625-word

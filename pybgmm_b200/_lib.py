@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BGMM_B200_LIB", os.path.join(HERE, "lib", "libbgmm_b200.so"))
 
-BGMM_OK, BGMM_EINVAL, BGMM_ENODEV, BGMM_EKMAX, BGMM_ENUMERIC, BGMM_ENOMEM = 0, -1, -2, -3, -4, -5
+BGMM_OK, BGMM_EINVAL, BGMM_ENODEV, BGMM_EKMAX, BGMM_ENUMERIC, BGMM_ENOMEM, BGMM_EWATCHDOG = 0, -1, -2, -3, -4, -5, -6
 COV_FULL, COV_DIAG = 0, 1
 
 EXPORTS = (
@@ -20,7 +20,7 @@ EXPORTS = (
     "bgmm_set_assignments", "bgmm_sweep", "bgmm_sweep_dev", "bgmm_set_engine", "bgmm_seed", "bgmm_get_uniforms",
     "bgmm_sweep_index", "bgmm_get_state", "bgmm_get_assignments_dev", "bgmm_K", "bgmm_log_prior",
     "bgmm_log_post_pred", "bgmm_log_marg_k", "bgmm_log_marg", "bgmm_add_item", "bgmm_del_item", "bgmm_mt19937_fill",
-    "bgmm_set_true_labels", "bgmm_contingency", "bgmm_cluster_ssq",
+    "bgmm_set_true_labels", "bgmm_contingency", "bgmm_cluster_ssq", "bgmm_set_label", "bgmm_set_state", "bgmm_set_guard",
 )
 
 
@@ -29,7 +29,8 @@ class SweepStats(C.Structure):
                 ("evals", C.c_int64), ("windows", C.c_int64), ("seq_data", C.c_int64), ("wasted", C.c_int64),
                 ("min_margin", C.c_double), ("device_ms", C.c_double), ("explicit_evals", C.c_int64),
                 ("refreshes", C.c_int64), ("generic_from", C.c_int64), ("phase_cycles", C.c_int64 * 16),
-                ("launches", C.c_int64), ("sweep_kernel_ms", C.c_double)]
+                ("launches", C.c_int64), ("sweep_kernel_ms", C.c_double), ("guard_hits", C.c_int64),
+                ("fast_steps", C.c_int64)]
 
     PHASES = ("stage", "head", "eval", "draw", "update", "scalars", "wineval", "barrier", "rare", "steps", "moves",
               "rounds")
@@ -86,6 +87,9 @@ def lib():
     L.bgmm_add_item.argtypes = [vp, C.c_int64, C.c_int32]
     L.bgmm_del_item.argtypes = [vp, C.c_int64]
     L.bgmm_set_component_stats.argtypes = [vp, C.c_int32, dp, dp, C.c_int64]
+    L.bgmm_set_label.argtypes = [vp, C.c_int64, C.c_int32]
+    L.bgmm_set_state.argtypes = [vp, ip, C.c_int32, dp, dp]
+    L.bgmm_set_guard.argtypes = [vp, C.c_double]
     L.bgmm_set_true_labels.argtypes = [vp, ip, C.c_int32]
     L.bgmm_contingency.argtypes = [vp, ip]
     L.bgmm_cluster_ssq.argtypes = [vp, dp]
@@ -271,6 +275,21 @@ class Chain(object):
         out = np.empty(max(self.K, 1), np.float64)
         _check(lib().bgmm_cluster_ssq(self._h, _dp(out)))
         return out[:self.K]
+
+    def set_label(self, i, k):
+        """Rewrite the label of datum i (-1: unassigned); no statistic changes (crpmm.py:84-85 does this on the host)."""
+        _check(lib().bgmm_set_label(self._h, int(i), int(k)))
+
+    def set_state(self, z, m_num=None, S_part=None):
+        """Labels, and optionally the exact bits of saved statistics (K x D, K x D x D | K x D)."""
+        z = np.ascontiguousarray(z, dtype=np.int64)
+        K = int(z.max()) + 1
+        m = None if m_num is None else np.ascontiguousarray(m_num[:K], dtype=np.float64)
+        S = None if S_part is None else np.ascontiguousarray(S_part[:K], dtype=np.float64)
+        _check(lib().bgmm_set_state(self._h, _ip(z), K, _dp(m), _dp(S)))
+
+    def set_guard(self, guard):
+        _check(lib().bgmm_set_guard(self._h, float(guard)))
 
     def add_item(self, i, k):
         _check(lib().bgmm_add_item(self._h, int(i), int(k)))

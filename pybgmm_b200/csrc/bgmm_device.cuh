@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdio.h>
 
 namespace bgmm {
 
@@ -72,6 +73,9 @@ struct Ctl {
     unsigned long long margin_bits;
     double gap;         // running estimate of the number of data between two movers
     long long explicit_evals, refreshes;
+    long long guard_hits;          // draws whose margin was below Params::guard and were redone on the exact path
+    long long fast_steps;          // data resolved by the register-resident sequential step (bgmm_seq.cuh)
+    long long watchdog_ns;         // spin loops give up (error word + trap) after this many ns of the global timer
     long long prof[16];            // phase clocks of CTA 0 (cycles), see bgmm_fast.cuh
     unsigned long long wsum[16], wcnt[16], wmax[16];  // evaluator unit clocks by category (profile builds)
 };
@@ -118,6 +122,8 @@ struct Params {
     int KS, Kcap;
     float win_factor;         // window length = win_factor x running gap between movers
     int near_zone;            // waiting rows within this many windows beyond the current one are kept current (env BGMM_NEAR)
+    double guard;             // a draw whose margin (probability units) is below this is redone exactly (0: never)
+    int *err;                 // device error word of the handle (set by set-up kernels: BGMM_E* code)
     int tune;                 // developer switches (env BGMM_TUNE): bit 0 = f_step evaluates with one thread per component,
                               // bit 1 = statistics by load / add / store instead of L2 reductions,
                               // bit 2 = rows about to enter the window are not kept current
@@ -139,6 +145,34 @@ __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) 
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Watchdog of the spin loops: wall-clock based (%globaltimer, ns), configurable (Ctl::watchdog_ns, env
+// BGMM_WATCHDOG_S on the host side), and independent of NDEBUG: a replica disagreement becomes an error word plus a
+// trap, never a hang.  The timer is polled once per 1024 spins.
+constexpr int E_WATCHDOG = -6;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+static __device__ __noinline__ void watchdog_fail(Ctl *c, int which) {
+    c->error = E_WATCHDOG;
+    __threadfence_system();
+    printf("bgmm watchdog %d: CTA %d waited longer than %lld ns (replicas stopped agreeing?)\n", which, (int)blockIdx.x,
+           c->watchdog_ns);
+    __trap();
+}
+struct SpinWatch {
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    __device__ __forceinline__ void poll(Ctl *c, int which) {
+        if ((++spins & 1023u) == 0u) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if ((long long)(now - t0) > c->watchdog_ns) watchdog_fail(c, which);
+        }
+    }
+};
+
 // Grid-wide barrier for a cooperative launch (all CTAs co-resident).  Sense-reversing on a generation word.
 __device__ __forceinline__ void grid_barrier(Ctl *c) {
     __syncthreads();
@@ -151,7 +185,8 @@ __device__ __forceinline__ void grid_barrier(Ctl *c) {
             __threadfence();
             st_release_u32(&c->bar_gen, gen + 1);
         } else {
-            while (ld_acquire_u32(&c->bar_gen) == gen) __nanosleep(32);
+            SpinWatch wd;
+            while (ld_acquire_u32(&c->bar_gen) == gen) { __nanosleep(32); wd.poll(c, 0); }
         }
         __threadfence();
     }

@@ -63,6 +63,19 @@ __global__ void k_philox(double *__restrict__ u, long long N, unsigned long long
     if (j < N) u[j] = philox_uniform(seed, sweep, (unsigned long long)j);
 }
 
+// The scan order must be a permutation of 0..N-1 (pcrpmm.py:89 draws np.random.permutation): an index out of range
+// would be an out-of-bounds read of X / z, and a repeated index would be visited twice while the replicas of the
+// resident engine still read the sweep-start label copy.  One pass: every index sets its bit; a bit already set or an
+// index out of range writes BGMM_EINVAL to the handle's error word (checked before the sweep kernel is launched).
+__global__ void k_check_perm(const long long *__restrict__ order, long long N, unsigned int *__restrict__ bits, int *err) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const long long i = order[j];
+    if (i < 0 || i >= N) { *err = BGMM_EINVAL; return; }
+    const unsigned int m = 1u << (i & 31);
+    if (atomicOr(bits + (i >> 5), m) & m) *err = BGMM_EINVAL;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Per-sweep record (GMM.update_record_dict, gmm/gmm.py:65-118) without moving the labels to the host.
 //
@@ -289,6 +302,7 @@ static int check_dev_err(bgmm_handle *h, const char *what) {
     if (e != 0) {
         int zero = 0;
         cudaMemcpyAsync(h->d_err, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+        if (e == BGMM_EINVAL) return fail(e, std::string(what) + ": the scan order is not a permutation of 0..N-1");
         return fail(e, std::string(what) + ": covariance not positive definite");
     }
     return 0;
@@ -327,6 +341,8 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
     bgmm_handle *h = new bgmm_handle();
     h->device = device; h->N = N; h->D = D; h->DP = pad_dim(D); h->cov = cov_type; h->K_max = K_max;
     h->k0 = k0; h->v0 = v0;
+    if (const char *g = getenv("BGMM_GUARD")) h->guard = atof(g);
+    if (const char *w = getenv("BGMM_WATCHDOG_S")) h->watchdog_ns = (long long)(atof(w) * 1e9);
     const int DP = h->DP;
     int (*prep)(bgmm_handle *) = nullptr;
     h->ops = pick_ops(cov_type, DP, &prep);
@@ -601,6 +617,8 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     CU(cudaStreamSynchronize(st));
     c.moves = c.births = c.deaths = c.evals = c.windows = c.seq_data = c.wasted = 0;
     c.explicit_evals = c.refreshes = 0;
+    c.guard_hits = c.fast_steps = 0;
+    c.watchdog_ns = h->watchdog_ns;
     memset(c.prof, 0, sizeof(c.prof));
     memset(c.wsum, 0, sizeof(c.wsum)); memset(c.wcnt, 0, sizeof(c.wcnt)); memset(c.wmax, 0, sizeof(c.wmax));
     const double one = 1.0;
@@ -613,6 +631,16 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     p.log_alpha = log(alpha); p.power = power;
     p.init_gap = h->last_gap;
     long long generic_from = -1;
+    if (d_order) {
+        // N bits of scratch: the relabel buffer is idle during a sweep
+        unsigned int *bits = (unsigned int *)h->d_tmp_ll;
+        CU(cudaMemsetAsync(bits, 0, sizeof(unsigned int) * (size_t)((h->N + 31) / 32), st));
+        const int T = 256;
+        k_check_perm<<<(unsigned)((h->N + T - 1) / T), T, 0, st>>>(d_order, h->N, bits, h->d_err);
+        CU(cudaGetLastError());
+        h->launches += 1;
+        if (int rc = check_dev_err(h, "sweep")) return rc;
+    }
     CU(cudaEventRecord(h->ev0, st));
     // engine 0..2: the replicated-state-machine engine (bgmm_fast.cuh) where it applies; 3..5: the generic engine
     bool fast = h->fast_ok && h->engine < 3 && c.K <= h->Kcap;
@@ -620,6 +648,9 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         // the replicas read the labels as they were at the start of the sweep; CTA 0 writes the other copy
         CU(cudaMemcpyAsync(h->d_z2, h->d_z, sizeof(int) * (size_t)h->N, cudaMemcpyDeviceToDevice, st));
         if (int rc = h->ops->fast_prep(h, p, c.K)) return rc;
+        // a component whose S_N is not positive definite stops the sweep here, before the kernel would run on a
+        // partially written record
+        if (int rc = check_dev_err(h, "sweep (record set-up)")) return rc;
         CU(cudaEventRecord(h->ev2, st));
         if (int rc = h->ops->fast_sweep(h, p)) return rc;
         CU(cudaEventRecord(h->ev3, st));
@@ -673,10 +704,13 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
                             (double)c.wsum[t] / (double)c.wcnt[t], c.wmax[t]);
         }
         out->launches = h->launches; out->sweep_kernel_ms = ms_k;
+        out->guard_hits = c.guard_hits; out->fast_steps = c.fast_steps;
     }
     if (c.error == BGMM_EKMAX) return fail(BGMM_EKMAX, "a new component would exceed K_max (the reference raises IndexError)");
     if (c.error != 0) return fail(c.error, "sweep: non-finite weights or covariance not positive definite");
-    return 0;
+    // the records the auxiliary entry points use were rebuilt after the sweep: report a failure of that rebuild now,
+    // not from whichever call happens to look next
+    return check_dev_err(h, "sweep (records after the sweep)");
 }
 
 int bgmm_sweep_dev(bgmm_t *h, const int64_t *d_order, const double *d_uniforms, double alpha, double power,
@@ -962,6 +996,36 @@ int bgmm_set_component_stats(bgmm_t *h, int32_t k, const double *m_num, const do
     if (int rc = h->ops->refactor_all(h, p, k, 1)) return rc;
     CU(cudaStreamSynchronize(st));
     return check_dev_err(h, "set_component_stats");
+}
+int bgmm_set_label(bgmm_t *h, int64_t i, int32_t k) {
+    if (!h) return fail(BGMM_EINVAL, "handle is NULL");
+    if (i < 0 || i >= h->N) return fail(BGMM_EINVAL, "datum index out of range");
+    if (k < -1 || k >= h->K) return fail(BGMM_EINVAL, "component index out of range");
+    CU(cudaSetDevice(h->device));
+    int uid = -1;
+    if (k >= 0) CU(cudaMemcpyAsync(&uid, h->d_uid_of_slot + k, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(h->d_z + i, &uid, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int bgmm_set_state(bgmm_t *h, const int64_t *z, int32_t K, const double *m_num, const double *S_part) {
+    if (!h || !z) return fail(BGMM_EINVAL, "NULL argument");
+    if (int rc = bgmm_set_assignments(h, z)) return rc;
+    if (K != h->K) return fail(BGMM_EINVAL, "K does not match the labels");
+    if (!m_num && !S_part) return 0;
+    if (!m_num || !S_part) return fail(BGMM_EINVAL, "m_num and S_part must be given together");
+    std::vector<long long> cnt(h->K_max);
+    CU(cudaMemcpy(cnt.data(), h->d_counts, sizeof(long long) * h->K_max, cudaMemcpyDeviceToHost));
+    const size_t ssr = (h->cov == BGMM_COV_FULL) ? (size_t)h->D * h->D : (size_t)h->D;
+    for (int k = 0; k < K; ++k)
+        if (int rc = bgmm_set_component_stats(h, k, m_num + (size_t)k * h->D, S_part + (size_t)k * ssr, cnt[k])) return rc;
+    return 0;
+}
+int bgmm_set_guard(bgmm_t *h, double guard) {
+    if (!h || !(guard >= 0.0) || !(guard < 1.0)) return fail(BGMM_EINVAL, "guard must be in [0, 1)");
+    h->guard = guard;
+    return 0;
 }
 int bgmm_add_item(bgmm_t *h, int64_t i, int32_t k) { return item_op(h, 1, i, k); }
 int bgmm_del_item(bgmm_t *h, int64_t i) { return item_op(h, 0, i, 0); }

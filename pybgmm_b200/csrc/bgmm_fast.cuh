@@ -26,7 +26,6 @@
 #pragma once
 #include "bgmm_sweep.cuh"
 #include "bgmm_fastmath.cuh"
-#include <assert.h>
 
 namespace bgmm {
 namespace fast {
@@ -139,10 +138,8 @@ static __device__ __noinline__ void f_grid_barrier(Ctl *c) {
             __threadfence();
             st_release_u32(&c->bar_gen, gen + 1);
         } else {
-            const long long t0 = clock64();
-            while (ld_acquire_u32(&c->bar_gen) == gen) {
-                if (clock64() - t0 > 8000000000LL) assert(false && "bgmm watchdog 1: replicas stopped agreeing");
-            }
+            SpinWatch wd;
+            while (ld_acquire_u32(&c->bar_gen) == gen) wd.poll(c, 1);
         }
         __threadfence();
     }
@@ -157,6 +154,8 @@ struct FSh {
     long long pos;
     double gap;
     long long moves, births, deaths, evals, windows, seq_data, wasted, explicit_evals, refreshes;
+    long long guard_hits, fast_steps;
+    double last_mg;          // margin of the draw just made (f_step)
     unsigned long long margin_bits;
     // datum being resolved
     int k_new, need_explicit, explicit_done, refresh_a, refresh_b;
@@ -205,11 +204,9 @@ static __device__ __noinline__ void f_round_barrier(Ctl *c, const unsigned long 
             c->rb_count = 0;
             st_release_u64(&c->rb_word, (want << 44) | res);
         } else {
-            const long long t0 = clock64();
+            SpinWatch wd;
             unsigned long long w;
-            while (((w = ld_acquire_u64(&c->rb_word)) >> 44) != want) {
-                if (clock64() - t0 > 8000000000LL) assert(false && "bgmm watchdog 4: replicas stopped agreeing");
-            }
+            while (((w = ld_acquire_u64(&c->rb_word)) >> 44) != want) wd.poll(c, 4);
             res = w & M44;
         }
         *fv_out = res;
@@ -858,11 +855,97 @@ __device__ __noinline__ void f_log_domain_draw(const Params &p, const FSmem<DP> 
         const int k = f_warp_draw_log(ew, K + 1, u, &mg);
         if (lane == 0) {
             sh.k_new = k;
+            sh.last_mg = mg;
             if (k < 0) sh.error = -4;
-            sh.evals += K;
-            const unsigned long long mb = (unsigned long long)__double_as_longlong(mg);
-            if (mb < sh.margin_bits) sh.margin_bits = mb;
         }
+    }
+    __syncthreads();
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Margin guard.  The engine's weights differ from the reference's by rounding (Sherman-Morrison records, table-driven
+// log / exp, a different summation order: ~1e-12 in probability units at worst), so a draw is the reference's draw only
+// while the uniform keeps a distance from the boundaries of the drawn interval.  When that margin is below
+// Params::guard the datum is redone on the exact path (every CTA identically):
+//   * every live record is rebuilt from the bit-exact statistics (what the start of a sweep does), the datum's own
+//     component with the datum removed by the reference's del_item arithmetic (gaussian_components.py:184-185);
+//   * weights in the log domain with libdevice log, normalised like crpmm.py:75 (exp(w - logsumexp(w))), and the
+//     reference's sequential-subtract draw (utils.py:15-20) by one thread.
+// Leaves the drawn index in sh.k_new and the reduced own component in tmprec (the caller treats it as `expl`).
+// ---------------------------------------------------------------------------------------------
+template <int DP, int ST>
+__device__ __noinline__ double f_weight_exact(const double *__restrict__ col, const double *__restrict__ x) {
+    using Ly = Lay<DP>;
+    double d[DP];
+#pragma unroll
+    for (int a = 0; a < DP; ++a) d[a] = col[(Ly::MU + a) * ST] - x[a];
+    double q = 0.0;
+#pragma unroll
+    for (int a = 0; a < DP; ++a) {
+        double r = 0.0;
+#pragma unroll
+        for (int b = 0; b < a; ++b) r = fma(col[(a * (a + 1) / 2 + b) * ST], d[b], r);
+        r = fma(0.5 * col[(a * (a + 1) / 2 + a) * ST], d[a], r);
+        q = fma(d[a], r, q);
+    }
+    q *= 2.0;
+    const double *sc = col + Ly::SC * ST;
+    return sc[F_CW * ST] - sc[F_H * ST] * log(1.0 + sc[F_G * ST] * q);
+}
+
+template <int DP>
+__device__ __noinline__ void f_exact_redo(const Params &p, const FSmem<DP> &s, int K, int k_old, double n_old,
+                                          bool own_live, const double *xs, double wref, double u, double *ew) {
+    using Ly = Lay<DP>;
+    constexpr int ST = Ly::KS;
+    FSh &sh = *s.sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    f_grid_barrier(p.ctl);   // CTA 0's statistics are complete and stay frozen until the second barrier
+    if (warp == 0) {
+        bool okf = true;
+        for (int k = 0; k < K && okf; ++k) {
+            const double n_k = s.rec[(Ly::SC + F_N) * ST + k];
+            okf = f_exact_record_warp<DP>(p, 0, p.num + (size_t)k * DP, p.S + (size_t)k * Ly::PP, n_k, nullptr, s.rc, s.A,
+                                          s.W, s.mm, s.rec + k, ST);
+        }
+        if (okf && own_live)
+            okf = f_exact_record_warp<DP>(p, 0, p.num + (size_t)k_old * DP, p.S + (size_t)k_old * Ly::PP, n_old - 1.0, xs,
+                                          s.rc, s.A, s.W, s.mm, s.tmprec, 1);
+        if (lane == 0) {
+            if (!okf) sh.error = -4;
+            sh.guard_hits += 1;
+            sh.refreshes += K;
+            // every record changed (by rounding): cached rows of the window evaluators are void
+            sh.ver += 1;
+            sh.dall_ver = sh.ver;
+        }
+    }
+    f_grid_barrier(p.ctl);
+    if (sh.error) return;
+    if (tid < K) {
+        ew[tid] = ((own_live && tid == k_old) ? f_weight_exact<DP, 1>(s.tmprec, xs) : f_weight_exact<DP, ST>(s.rec + tid, xs)) -
+                  wref;
+    } else if (tid == K) {
+        ew[K] = 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double M = -INFINITY;
+        for (int k = 0; k <= K; ++k) M = fmax(M, ew[k]);
+        double ssum = 0.0;
+        for (int k = 0; k <= K; ++k) ssum += exp(ew[k] - M);
+        const double lse = M + log(ssum);
+        double t = u, mg = 0.0;
+        int kk = K;   // utils.py:20: the last index when the running value never goes negative
+        for (int k = 0; k <= K; ++k) {
+            const double tb = t;
+            t -= exp(ew[k] - lse);
+            if (t < 0.0) { kk = k; mg = fmin(fabs(tb), -t); break; }
+        }
+        if (!(ssum > 0.0) || !(ssum < INFINITY)) { kk = -2; sh.error = -4; }
+        sh.k_new = kk;
+        sh.last_mg = mg;
     }
     __syncthreads();
 }
@@ -1077,6 +1160,7 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
 
     // phase B: the draw (crpmm.py:75-78, utils.py:7-20): first index whose cumulative sum exceeds u * total
     int k_drawn;
+    double mg_draw = 0.0;   // margin of the draw (uniform over the CTA)
     if (cta_draw) {
         const double w0 = sh.wtot[0], w1 = sh.wtot[1], w2 = sh.wtot[2], w3 = sh.wtot[3];
         const double p1 = w0, p2 = w0 + w1, p3 = p2 + w2, tot = p3 + w3;
@@ -1101,34 +1185,37 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
         else mg = sh.wmg[k >> 5];
         if (!(tot > 0.0) || !(tot < INFINITY)) k = -2;
         k_drawn = k;
-        if (tid == 0) {
-            sh.k_new = k;
-            if (k >= 0) {
-                sh.evals += K;
-                const unsigned long long mb = (unsigned long long)__double_as_longlong(mg);
-                if (mb < sh.margin_bits) sh.margin_bits = mb;
-            }
-        }
+        mg_draw = mg;
+        if (tid == 0) sh.k_new = k;
     } else {
         if (warp == 0) {
             double mg;
             const int k = f_warp_pick(ew, K + 1, s.ub[jj], &mg);
-            if (lane == 0) {
-                sh.k_new = k;
-                if (k >= 0) {
-                    sh.evals += K;
-                    const unsigned long long mb = (unsigned long long)__double_as_longlong(mg);
-                    if (mb < sh.margin_bits) sh.margin_bits = mb;
-                }
-            }
+            if (lane == 0) { sh.k_new = k; sh.last_mg = mg; }
         }
         __syncthreads();
         k_drawn = sh.k_new;
+        mg_draw = sh.last_mg;
     }
     if (k_drawn == -2) {
         if (cta_draw) __syncthreads();   // thread 0's sh.k_new = -2 must not land after the fallback's result
         f_log_domain_draw<DP>(p, s, K, k_old, own_live, expl, xs, wref, s.ub[jj], ew);
         k_drawn = sh.k_new;
+        mg_draw = sh.last_mg;
+    }
+    if (k_drawn >= 0 && mg_draw < p.guard) {
+        // the uniform is too close to a boundary of the drawn interval for the fast arithmetic: exact path
+        __syncthreads();
+        f_exact_redo<DP>(p, s, K, k_old, n_old, own_live, xs, wref, s.ub[jj], ew);
+        k_drawn = sh.k_new;
+        mg_draw = sh.last_mg;
+        expl = own_live;
+        F_PROF(PH_RARE);
+    }
+    if (tid == 0 && k_drawn >= 0) {
+        sh.evals += K;
+        const unsigned long long mb = (unsigned long long)__double_as_longlong(mg_draw);
+        if (mb < sh.margin_bits) sh.margin_bits = mb;
     }
     F_PROF(PH_DRAW);
     F_COUNT(PH_STEPS);
@@ -1371,7 +1458,9 @@ __device__ void f_window_eval(const Params &p, const FSmem<DP> &s, long long pos
                 k_new = f_warp_pick_inl(ew, K + 1, c.u, &mg);
                 F_WSUB_END(7);
             }
-            if (k_new != k_old) {
+            if (k_new >= 0 && mg < p.guard) {
+                cand = true;   // margin guard: the full step redoes this datum (on the exact path if it agrees)
+            } else if (k_new != k_old) {
                 cand = true;   // includes -2 (an untrusted / overflowed entry): the step redoes it in full
                 // a plain move between two live components needs no second evaluation if it turns out to be
                 // the first candidate: every datum in front of it stayed, so the records it saw are current
@@ -1492,8 +1581,9 @@ __device__ __noinline__ void f_bulk_eval(const Params &p, const FSmem<DP> &s, lo
             if (!ok || !(ssum < INFINITY) || !(t0 >= pre) || !(t0 < pre + eown)) {
                 cand = true;
             } else {
-                const double mg = fmin(t0 - pre, pre + eown - t0);
-                my_margin = fmin(my_margin, (double)__fdividef((float)mg, (float)ssum));
+                const double mg = (double)__fdividef((float)fmin(t0 - pre, pre + eown - t0), (float)ssum);
+                if (mg < p.guard) cand = true;   // margin guard: resolved in full by every CTA
+                else my_margin = fmin(my_margin, mg);
             }
         }
         if (cand) {
@@ -1548,6 +1638,8 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
         sh.gap = p.init_gap;
         sh.moves = sh.births = sh.deaths = sh.evals = sh.windows = sh.seq_data = sh.wasted = 0;
         sh.explicit_evals = sh.refreshes = 0;
+        sh.guard_hits = sh.fast_steps = 0;
+        sh.last_mg = 1.0;
         const double one = 1.0;
         sh.margin_bits = (unsigned long long)__double_as_longlong(one);
         sh.round = 0;
@@ -1596,9 +1688,9 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             }
         }
         uint32_t okw = 0;
-        const long long t0 = clock64();
+        SpinWatch wd;
         while (!okw) {
-            if (clock64() - t0 > 8000000000LL) assert(false && "bgmm watchdog 3: replicas stopped agreeing");
+            wd.poll(ctl, 3);
             asm volatile(
                 "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                 : "=r"(okw)
@@ -1739,6 +1831,8 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             __stcg(&ctl->wasted, __ldcg(&ctl->wasted) + sh.wasted);
             __stcg(&ctl->explicit_evals, __ldcg(&ctl->explicit_evals) + sh.explicit_evals);
             __stcg(&ctl->refreshes, __ldcg(&ctl->refreshes) + sh.refreshes);
+            __stcg(&ctl->guard_hits, __ldcg(&ctl->guard_hits) + sh.guard_hits);
+            __stcg(&ctl->fast_steps, __ldcg(&ctl->fast_steps) + sh.fast_steps);
             atomicMin(&ctl->margin_bits, sh.margin_bits);
             __stcg(&ctl->gap, sh.gap);
             for (int t = 0; t < PH_COUNT; ++t) __stcg(&ctl->prof[t], sh.prof[t]);

@@ -30,7 +30,7 @@ struct Sh {
     double margin;
     double u;
     // CTA 0's working copy of the control-block counters (loaded after barrier 1, stored before barrier 2)
-    long long moves, births, deaths, evals, windows, seq_data, wasted;
+    long long moves, births, deaths, evals, windows, seq_data, wasted, guard_hits;
     unsigned long long margin_bits;
     double gap;
     int n_free;
@@ -228,90 +228,103 @@ __device__ void resolve(const Params &p, const Smem &sm, long long j) {
 #pragma unroll
     for (int a = 0; a < DP; ++a) x[a] = sm.x[a];
 
-    // weights of the live components (crpmm.py:68-74)
-    for (int k = tid; k < K; k += blockDim.x) {
-        bool cg;
-        const double *rec = rec_ptr<DP, COV>(p, sm.rec, k, cg);
-        double w;
-        if (k == k_old && !died) {
-            bool ok = true;
-            w = cg ? weight_own_removed<DP, COV, true>(rec, x, p, &ok) : weight_own_removed<DP, COV, false>(rec, x, p, &ok);
-            if (!ok) sh.need_explicit = 1;
-        } else {
-            w = cg ? weight_other<DP, COV, true>(rec, x, p.D) : weight_other<DP, COV, false>(rec, x, p.D);
-        }
-        sm.w[k] = w;
-    }
-    if (tid == 0) sm.w[K] = p.log_alpha + p.log_prior[i];
-    __syncthreads();
-
-    const bool expl = sh.need_explicit != 0;
-    if (expl) {
-        // explicit del_item: save the statistics (scratch slot K_max), remove, refactor, re-evaluate the column
-        stats_copy<DP, COV>(p, p.K_max, k_old);
-        __syncthreads();
-        stats_axpy<DP, COV>(p, k_old, sm.x, -1);
-        if (tid == 0) __stcg(p.counts + k_old, n_old - 1);
-        __syncthreads();
-        if (warp == 0) {
-            const bool okf = refactor_warp<DP, COV>(p, p.num + (size_t)k_old * DP, p.S + (size_t)k_old * stat_len(DP, COV),
-                                                    n_old - 1, 0, p.rec + (size_t)k_old * R,
-                                                    k_old < p.Kc ? sm.rec + (size_t)k_old * R : nullptr, sm.A0);
-            if (!okf && lane == 0) sh.error = -4;
-        }
-        __syncthreads();
-        if (tid == 0) {
+    // Margin guard: when the uniform lands too close to a boundary of the drawn interval for the closed-form own
+    // weight (Params::guard), the datum is redone with the own component removed explicitly (the reference's own
+    // del_item arithmetic, gaussian_components.py:171-186) -- pass 1.
+    bool expl = false;
+    for (int pass = 0; pass < 2; ++pass) {
+        // weights of the live components (crpmm.py:68-74)
+        for (int k = tid; k < K; k += blockDim.x) {
             bool cg;
-            const double *rec = rec_ptr<DP, COV>(p, sm.rec, k_old, cg);
-            sm.w[k_old] = cg ? weight_other<DP, COV, true>(rec, x, p.D) : weight_other<DP, COV, false>(rec, x, p.D);
-            add_dirty(sh, k_old);
+            const double *rec = rec_ptr<DP, COV>(p, sm.rec, k, cg);
+            double w;
+            if (k == k_old && !died) {
+                bool ok = true;
+                w = cg ? weight_own_removed<DP, COV, true>(rec, x, p, &ok) : weight_own_removed<DP, COV, false>(rec, x, p, &ok);
+                if (!ok) sh.need_explicit = 1;
+            } else {
+                w = cg ? weight_other<DP, COV, true>(rec, x, p.D) : weight_other<DP, COV, false>(rec, x, p.D);
+            }
+            sm.w[k] = w;
+        }
+        if (tid == 0) sm.w[K] = p.log_alpha + p.log_prior[i];
+        __syncthreads();
+
+        if (sh.need_explicit != 0 && !expl) {
+            expl = true;
+            // explicit del_item: save the statistics (scratch slot K_max), remove, refactor, re-evaluate the column
+            stats_copy<DP, COV>(p, p.K_max, k_old);
+            __syncthreads();
+            stats_axpy<DP, COV>(p, k_old, sm.x, -1);
+            if (tid == 0) __stcg(p.counts + k_old, n_old - 1);
+            __syncthreads();
+            if (warp == 0) {
+                const bool okf = refactor_warp<DP, COV>(p, p.num + (size_t)k_old * DP, p.S + (size_t)k_old * stat_len(DP, COV),
+                                                        n_old - 1, 0, p.rec + (size_t)k_old * R,
+                                                        k_old < p.Kc ? sm.rec + (size_t)k_old * R : nullptr, sm.A0);
+                if (!okf && lane == 0) sh.error = -4;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                bool cg;
+                const double *rec = rec_ptr<DP, COV>(p, sm.rec, k_old, cg);
+                sm.w[k_old] = cg ? weight_other<DP, COV, true>(rec, x, p.D) : weight_other<DP, COV, false>(rec, x, p.D);
+                add_dirty(sh, k_old);
+            }
+            __syncthreads();
+        }
+
+        // logsumexp + draw (crpmm.py:75-78, utils.py:7-20) by warp 0 over the K+1 weights
+        if (warp == 0) {
+            const int n = K + 1;
+            const int per = (n + 31) / 32;
+            const int lo = lane * per, hi = min(n, lo + per);
+            double M = -INFINITY;
+            for (int k = lo; k < hi; ++k) M = fmax(M, sm.w[k]);
+    #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
+            double sl = 0.0;
+            for (int k = lo; k < hi; ++k) {
+                const double dlt = sm.w[k] - M;
+                const double e = (dlt < EXP_CUTOFF) ? 0.0 : exp(dlt);
+                sm.w[k] = e;
+                sl += e;
+            }
+            double inc = sl;
+    #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const double s = __shfl_sync(0xffffffffu, inc, 31);
+            double t = sh.u * s - (inc - sl);
+            int cand = 0x7fffffff;
+            double marg = 1.0;
+            for (int k = lo; k < hi; ++k) {
+                const double tb = t;
+                t -= sm.w[k];
+                if (t < 0.0) { cand = k; marg = fmin(fabs(tb), -t) / s; break; }
+            }
+            int best = cand;
+    #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            const unsigned who = __ballot_sync(0xffffffffu, cand == best && cand != 0x7fffffff);
+            if (best == 0x7fffffff) {
+                if (lane == 0) { sh.k_new = K; sh.margin = 0.0; }  // utils.py:20 fallback: the last index
+            } else if (lane == (int)(__ffs(who) - 1)) {
+                sh.k_new = best; sh.margin = marg;
+            }
+            if (!(s > 0.0) || !(s < INFINITY)) { if (lane == 0) sh.error = -4; }
         }
         __syncthreads();
+        if (pass == 0 && !expl && k_old >= 0 && !died && sh.margin < p.guard && sh.error == 0) {
+            __syncthreads();
+            if (tid == 0) { sh.need_explicit = 1; sh.guard_hits += 1; }
+            __syncthreads();
+            continue;
+        }
+        break;
     }
-
-    // logsumexp + draw (crpmm.py:75-78, utils.py:7-20) by warp 0 over the K+1 weights
-    if (warp == 0) {
-        const int n = K + 1;
-        const int per = (n + 31) / 32;
-        const int lo = lane * per, hi = min(n, lo + per);
-        double M = -INFINITY;
-        for (int k = lo; k < hi; ++k) M = fmax(M, sm.w[k]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
-        double sl = 0.0;
-        for (int k = lo; k < hi; ++k) {
-            const double dlt = sm.w[k] - M;
-            const double e = (dlt < EXP_CUTOFF) ? 0.0 : exp(dlt);
-            sm.w[k] = e;
-            sl += e;
-        }
-        double inc = sl;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        const double s = __shfl_sync(0xffffffffu, inc, 31);
-        double t = sh.u * s - (inc - sl);
-        int cand = 0x7fffffff;
-        double marg = 1.0;
-        for (int k = lo; k < hi; ++k) {
-            const double tb = t;
-            t -= sm.w[k];
-            if (t < 0.0) { cand = k; marg = fmin(fabs(tb), -t) / s; break; }
-        }
-        int best = cand;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-        const unsigned who = __ballot_sync(0xffffffffu, cand == best && cand != 0x7fffffff);
-        if (best == 0x7fffffff) {
-            if (lane == 0) { sh.k_new = K; sh.margin = 0.0; }  // utils.py:20 fallback: the last index
-        } else if (lane == (int)(__ffs(who) - 1)) {
-            sh.k_new = best; sh.margin = marg;
-        }
-        if (!(s > 0.0) || !(s < INFINITY)) { if (lane == 0) sh.error = -4; }
-    }
-    __syncthreads();
     const int k_new = sh.k_new;
     if (tid == 0) {
         sh.evals += K;
@@ -510,7 +523,7 @@ __device__ void window_eval(const Params &p, const Smem &sm, long long pos, long
                     if (t < 0.0) { k_new = k; marg = fmin(fabs(tb), -t) / s; hit = true; break; }
                 }
                 if (!hit) { const double tb = t; t -= eK; marg = (t < 0.0) ? fmin(fabs(tb), -t) / s : 0.0; }
-                if (k_new != k_old || !(s > 0.0) || !(s < INFINITY)) flag = true;
+                if (k_new != k_old || !(s > 0.0) || !(s < INFINITY) || marg < p.guard) flag = true;
                 else my_margin = fmin(my_margin, marg);
             }
         }
@@ -595,6 +608,7 @@ __global__ void __launch_bounds__(T_SWEEP, 1) k_sweep(const Params p) {
                 sh.moves = __ldcg(&ctl->moves); sh.births = __ldcg(&ctl->births); sh.deaths = __ldcg(&ctl->deaths);
                 sh.evals = __ldcg(&ctl->evals); sh.windows = __ldcg(&ctl->windows);
                 sh.seq_data = __ldcg(&ctl->seq_data); sh.wasted = __ldcg(&ctl->wasted);
+                sh.guard_hits = __ldcg(&ctl->guard_hits);
                 sh.margin_bits = __ldcg(&ctl->margin_bits); sh.gap = __ldcg(&ctl->gap);
                 sh.n_free = __ldcg(&ctl->n_free);
                 sh.n_old = __ldcg(&ctl->first);  // broadcast slot
@@ -648,6 +662,7 @@ __global__ void __launch_bounds__(T_SWEEP, 1) k_sweep(const Params p) {
                 __stcg(&ctl->moves, sh.moves); __stcg(&ctl->births, sh.births); __stcg(&ctl->deaths, sh.deaths);
                 __stcg(&ctl->evals, sh.evals); __stcg(&ctl->windows, sh.windows);
                 __stcg(&ctl->seq_data, sh.seq_data); __stcg(&ctl->wasted, sh.wasted);
+                __stcg(&ctl->guard_hits, sh.guard_hits);
                 __stcg(&ctl->margin_bits, sh.margin_bits);
                 __stcg(&ctl->n_free, sh.n_free);
                 if (sh.error) __stcg(&ctl->error, sh.error);

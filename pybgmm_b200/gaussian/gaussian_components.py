@@ -18,6 +18,32 @@ from .. import _lib
 DEFAULT_K_MAX = 1024
 
 
+class _LabelView(np.ndarray):
+    """`components.assignments` as the reference exposes it: an int array the caller may write a label into.  The
+    reference's restore path ends with `components.assignments[i] = k_old` on the host (crpmm.py:84-85); here that
+    assignment is written through to the label on the device (bgmm_set_label), so the protocol
+    cache_component_stats / del_item / restore_component_from_stats / assignments[i] = k leaves the device state
+    consistent.  Only the object handed out by the property writes through; copies and slices are plain arrays."""
+
+    def __new__(cls, labels, owner):
+        obj = np.asarray(labels).view(cls)
+        obj._owner = owner
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._owner = None
+
+    def __setitem__(self, index, value):
+        np.ndarray.__setitem__(self, index, value)
+        owner = self._owner
+        if owner is not None:
+            touched = np.arange(self.shape[0])[index]
+            for i in np.atleast_1d(touched):
+                owner._chain.set_label(int(i), int(np.ndarray.__getitem__(self, int(i))))
+            owner._cache = None
+            owner._counts = None
+
+
 class _DeviceComponents(object):
     _COV = "full"
 
@@ -28,6 +54,11 @@ class _DeviceComponents(object):
         self.N, self.D = X.shape
         if K_max is None:
             K_max = min(self.N, DEFAULT_K_MAX)
+            if self.N > DEFAULT_K_MAX:
+                import warnings
+                warnings.warn("K_max defaults to %d here (the reference's default is N = %d, which allocates three "
+                              "N x D x D arrays); a sweep that needs more components raises IndexError -- pass K_max "
+                              "explicitly" % (DEFAULT_K_MAX, self.N), stacklevel=3)
         self.K_max = int(K_max)
         self._check_prior()
         self._chain = _lib.Chain(X, prior.m_0, prior.k_0, prior.v_0, prior.S_0, self.K_max,
@@ -78,7 +109,7 @@ class _DeviceComponents(object):
     @property
     def assignments(self):
         if self._labels is None:
-            self._labels = self._chain.assignments()
+            self._labels = _LabelView(self._chain.assignments(), self)
         return self._labels
 
     # ---- per-sweep record on the device (no label traffic) ---------------------------------------

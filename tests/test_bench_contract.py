@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600,
+                        "--warmup", "1", "--rows", "1500"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600,
                        cwd=ROOT)
     assert r.returncode == 0
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]

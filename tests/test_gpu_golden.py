@@ -108,6 +108,23 @@ def test_cache_restore_protocol(gpu_lib):
     np.testing.assert_array_equal(after["S_part"], before["S_part"])
     np.testing.assert_array_equal(after["counts"], before["counts"])
     np.testing.assert_allclose(after["logdet"], before["logdet"], rtol=1e-14)
+    # the reference completes the restore on the host: components.assignments[i] = k_old (crpmm.py:84-85); here that
+    # assignment is written through to the device label
+    assert c.chain.assignments()[7] == -1
+    c.assignments[7] = k_old
+    np.testing.assert_array_equal(c.chain.assignments(), before["z"])
+    np.testing.assert_array_equal(c.assignments, before["z"])
+    # ... so a following sweep starts from a consistent state: same chain as an oracle that never took the detour
+    from oracle import oracle as O
+    orc = O.Oracle(X, m_0, k_0, v_0, S_0, K_max=8)
+    orc.set_assignments(np.arange(40) % 3)
+    u = np.random.RandomState(5).random_sample(40)
+    so = orc.sweep(u, 1.0)
+    sg = c.chain.sweep(1.0, 1.0, None, u)
+    assert (sg.K, sg.moves, sg.births, sg.deaths) == (so.K_end, so.moves, so.births, so.deaths)
+    np.testing.assert_array_equal(c.chain.assignments(), orc.assignments)
+    np.testing.assert_array_equal(c.chain.get_state()["counts"], orc.counts)
+    np.testing.assert_array_equal(c.chain.get_state()["S_part"], orc.S_N_partials)
 
 
 def test_errors_match_reference_conventions(gpu_lib):

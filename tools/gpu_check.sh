@@ -1,8 +1,19 @@
 #!/bin/bash
+# One GPU-box call: the -m gpu suite, then the default bench (C3) and short probes of the other configs.
+# usage (from the repo root, under gpurun):  bash tools/gpu_check.sh [tests|bench|all]
+what=${1:-all}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-timeout 300 python tools/perf_probe.py --sweeps 4 > gpurun_out/probe.log 2>&1; echo "probe rc=$?"
-grep -o "^sweep [0-9]*\|'moves': [0-9]*\|'windows': [0-9]*\|'seq_data': [0-9]*\|'sweep_kernel_ms': [0-9.]*" gpurun_out/probe.log | paste - - - - - 
-BGMM_WPROF=1 BGMM_B200_LIB=$PWD/pybgmm_b200/lib/libbgmm_b200_prof.so timeout 300 python tools/perf_probe.py --sweeps 4 > gpurun_out/probe_prof.log 2>&1
-grep "phases\|unit" gpurun_out/probe_prof.log | cut -c1-420
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+if [ "$what" = tests ] || [ "$what" = all ]; then
+  timeout 1500 python -m pytest tests -m gpu -x -q --timeout 900 --durations=8 > gpurun_out/pytest_gpu.log 2>&1
+  echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+  tail -15 gpurun_out/pytest_gpu.log
+fi
+if [ "$what" = bench ] || [ "$what" = all ]; then
+  timeout 900 python bench.py > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "bench c3 rc=$?"
+  cut -c1-1500 gpurun_out/bench_c3.json
+  timeout 600 python bench.py --workload c2 --no-cpu > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench c2 rc=$?"
+  cut -c1-900 gpurun_out/bench_c2.json
+  timeout 600 python bench.py --workload c5 --no-cpu > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "bench c5 rc=$?"
+  cut -c1-900 gpurun_out/bench_c5.json
+fi
