@@ -106,6 +106,21 @@ int bgmm_sweep(bgmm_t *h, const int64_t *order, const double *uniforms, double a
 /* Same, with `d_order` / `d_uniforms` already resident in device memory (either may be NULL as above). */
 int bgmm_sweep_dev(bgmm_t *h, const int64_t *d_order, const double *d_uniforms, double alpha, double power,
                    bgmm_sweep_stats *out);
+/*
+ * Many independent chains on one GPU (no counterpart in the reference, which runs one chain in one Python process;
+ * BASELINE.json configs[3] "8 independent chains" is the multi-GPU form of the same fan-out).
+ *   bgmm_fork        a new chain on the SAME data and prior as `parent`: shares the device copy of X, the cached log
+ *                    prior and the tables; own labels, statistics and RNG state.  All data start unassigned.  The shared
+ *                    buffers live until the last chain of the family is destroyed.
+ *   bgmm_sweep_many  one sweep (crpmm.py:57-88 / pcrpmm.py:93-131) of each of the n chains with ONE kernel launch, one
+ *                    thread block per chain; d_orders / d_uniforms are arrays of n DEVICE pointers (either array, or any
+ *                    entry, may be NULL with the meaning of bgmm_sweep).  Every chain walks exactly the chain bgmm_sweep
+ *                    would walk for the same inputs.  The chains must share device, stream, D, covariance type and K_max
+ *                    (full covariance, D <= 16).  out: n entries, or NULL.
+ */
+int bgmm_fork(bgmm_t *parent, bgmm_t **out);
+int bgmm_sweep_many(bgmm_t *const *handles, int32_t n, const int64_t *const *d_orders, const double *const *d_uniforms,
+                    double alpha, double power, bgmm_sweep_stats *out);
 /* Engine policy: 0 = adaptive (default), 1 = always the sequential per-datum path, 2 = always speculative windows;
  * 3..5 = the same three policies on the generic engine (any D, any K_max) instead of the shared-memory-resident one. */
 int bgmm_set_engine(bgmm_t *h, int32_t mode);

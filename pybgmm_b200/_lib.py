@@ -21,6 +21,7 @@ EXPORTS = (
     "bgmm_sweep_index", "bgmm_get_state", "bgmm_get_assignments_dev", "bgmm_K", "bgmm_log_prior",
     "bgmm_log_post_pred", "bgmm_log_marg_k", "bgmm_log_marg", "bgmm_add_item", "bgmm_del_item", "bgmm_mt19937_fill",
     "bgmm_set_true_labels", "bgmm_contingency", "bgmm_cluster_ssq", "bgmm_set_label", "bgmm_set_state", "bgmm_set_guard",
+    "bgmm_fork", "bgmm_sweep_many",
 )
 
 
@@ -90,6 +91,9 @@ def lib():
     L.bgmm_set_label.argtypes = [vp, C.c_int64, C.c_int32]
     L.bgmm_set_state.argtypes = [vp, ip, C.c_int32, dp, dp]
     L.bgmm_set_guard.argtypes = [vp, C.c_double]
+    L.bgmm_fork.argtypes = [vp, C.POINTER(vp)]
+    L.bgmm_sweep_many.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(vp), C.POINTER(vp), C.c_double, C.c_double,
+                                  C.POINTER(SweepStats)]
     L.bgmm_set_true_labels.argtypes = [vp, ip, C.c_int32]
     L.bgmm_contingency.argtypes = [vp, ip]
     L.bgmm_cluster_ssq.argtypes = [vp, dp]
@@ -158,6 +162,16 @@ class Chain(object):
                                  self.K_max, _dp(lg), _dp(lv), 0 if lg is None else len(lg), int(device), C.byref(h)))
         self._h = h
         self._ss = self.D * self.D if self.cov == COV_FULL else self.D
+
+    def fork(self):
+        """A new chain on the same data and prior: shares the device copy of X, the cached log prior and the tables
+        (bgmm_fork); own labels, statistics and RNG state.  All data start unassigned."""
+        other = object.__new__(Chain)
+        other.N, other.D, other.cov, other.K_max, other._ss = self.N, self.D, self.cov, self.K_max, self._ss
+        h = C.c_void_p()
+        _check(lib().bgmm_fork(self._h, C.byref(h)))
+        other._h = h
+        return other
 
     def close(self):
         if getattr(self, "_h", None):
@@ -296,3 +310,39 @@ class Chain(object):
 
     def del_item(self, i):
         _check(lib().bgmm_del_item(self._h, int(i)))
+
+
+class ChainGroup(object):
+    """Independent chains resident on one GPU that are advanced together: one kernel launch per sweep, one thread block
+    per chain (bgmm_sweep_many).  The chains must share device, stream, D, covariance type and K_max -- e.g. a chain and
+    its forks.  Every chain walks exactly the chain `Chain.sweep_dev` would walk for the same inputs."""
+
+    def __init__(self, chains):
+        self.chains = list(chains)
+        self._hs = (C.c_void_p * len(self.chains))(*[c._h for c in self.chains])
+
+    def __len__(self):
+        return len(self.chains)
+
+    def _ptrs(self, d):
+        """None, a list of device addresses (0 / None allowed), or a 2-D torch tensor (one row per chain)."""
+        n = len(self.chains)
+        if d is None:
+            return None
+        if hasattr(d, "data_ptr"):
+            assert d.dim() == 2 and d.shape[0] == n and d.is_contiguous()
+            step = d.shape[1] * d.element_size()
+            addrs = [d.data_ptr() + c * step for c in range(n)]
+        else:
+            addrs = [int(a) if a else None for a in d]
+            assert len(addrs) == n
+        return (C.c_void_p * n)(*addrs)
+
+    def sweep_dev(self, alpha, power=1.0, d_orders=None, d_uniforms=None):
+        """One sweep of every chain.  d_orders / d_uniforms: per-chain DEVICE buffers (see _ptrs), or None (data order /
+        each chain's own Philox stream).  Returns the per-chain SweepStats."""
+        n = len(self.chains)
+        out = (SweepStats * n)()
+        _check(lib().bgmm_sweep_many(self._hs, n, self._ptrs(d_orders), self._ptrs(d_uniforms), float(alpha),
+                                     float(power), out))
+        return list(out)

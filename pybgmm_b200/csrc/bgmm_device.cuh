@@ -124,6 +124,11 @@ struct Params {
     int near_zone;            // waiting rows within this many windows beyond the current one are kept current (env BGMM_NEAR)
     double guard;             // a draw whose margin (probability units) is below this is redone exactly (0: never)
     int *err;                 // device error word of the handle (set by set-up kernels: BGMM_E* code)
+    float gap_to_win, gap_to_seq;  // mode switches of the resident engine: windows from this gap between movers up,
+                              // sequential steps from this gap down (env BGMM_GAP_WIN / BGMM_GAP_SEQ)
+    int solo;                 // 1: this CTA is the chain's only replica (bgmm_sweep_many: one chain per CTA) -- grid
+                              // barriers become CTA barriers, the sequential engine only
+    int writer;               // set per CTA by the kernel: this CTA writes the chain's global state (CTA 0, or solo)
     int tune;                 // developer switches (env BGMM_TUNE): bit 0 = f_step evaluates with one thread per component,
                               // bit 1 = statistics by load / add / store instead of L2 reductions,
                               // bit 2 = rows about to enter the window are not kept current

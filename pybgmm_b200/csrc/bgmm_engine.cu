@@ -283,16 +283,77 @@ static const Ops *pick_ops(int cov, int DP, int (**prep)(bgmm_handle *)) {
 }
 
 static void free_all(bgmm_handle *h) {
-    cudaFree(h->dX); cudaFree(h->d_log_prior); cudaFree(h->d_lgam); cudaFree(h->d_logv); cudaFree(h->d_m0);
-    cudaFree(h->d_S0); cudaFree(h->d_z); cudaFree(h->d_slot_of_uid); cudaFree(h->d_uid_of_slot); cudaFree(h->d_uid_free);
+    // per-chain state
+    cudaFree(h->d_z); cudaFree(h->d_slot_of_uid); cudaFree(h->d_uid_of_slot); cudaFree(h->d_uid_free);
     cudaFree(h->d_counts); cudaFree(h->d_num); cudaFree(h->d_S); cudaFree(h->d_rec); cudaFree(h->d_wbuf);
     cudaFree(h->d_rec_prior); cudaFree(h->d_ctl); cudaFree(h->d_err); cudaFree(h->d_u); cudaFree(h->d_order);
-    cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf); cudaFree(h->d_ntab); cudaFree(h->d_fmtab);
-    cudaFree(h->d_true); cudaFree(h->d_table);
+    cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf);
+    cudaFree(h->d_true); cudaFree(h->d_table); cudaFree(h->d_pv);
+    // buffers shared with the chains forked from / with this one: freed with the last of them
+    if (h->sb && --h->sb->refs == 0) {
+        SharedBufs *b = h->sb;
+        cudaFree(b->dX); cudaFree(b->d_log_prior); cudaFree(b->d_lgam); cudaFree(b->d_logv); cudaFree(b->d_m0);
+        cudaFree(b->d_S0); cudaFree(b->d_ntab); cudaFree(b->d_fmtab);
+        delete b;
+    }
+    h->sb = nullptr;
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev3) cudaEventDestroy(h->ev3);
+}
+
+// per-chain device state (labels, uid tables, statistics, records, control block, scratch): bgmm_create and bgmm_fork
+static int alloc_chain_state(bgmm_handle *h) {
+    const long long N = h->N;
+    const int DP = h->DP, K_max = h->K_max;
+    const int SS = stat_len(DP, h->cov), R = h->ops->rec_len;
+#define ALLOC(ptr, bytes)                                                                             \
+    do {                                                                                              \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                                        \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(BGMM_ENOMEM, std::string("cudaMalloc ") + #ptr + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+    ALLOC(h->d_z, sizeof(int) * (size_t)N);
+    ALLOC(h->d_slot_of_uid, sizeof(int) * K_max);
+    ALLOC(h->d_uid_of_slot, sizeof(int) * K_max);
+    ALLOC(h->d_uid_free, sizeof(int) * K_max);
+    ALLOC(h->d_counts, sizeof(long long) * (K_max + 1));
+    ALLOC(h->d_num, sizeof(double) * (size_t)(K_max + 1) * DP);
+    ALLOC(h->d_S, sizeof(double) * (size_t)(K_max + 1) * SS);
+    ALLOC(h->d_rec, sizeof(double) * (size_t)(K_max + 1) * R);
+    ALLOC(h->d_rec_prior, sizeof(double) * R);
+    ALLOC(h->d_ctl, sizeof(Ctl));
+    ALLOC(h->d_err, sizeof(int));
+    ALLOC(h->d_u, sizeof(double) * (size_t)N);
+    ALLOC(h->d_order, sizeof(long long) * (size_t)N);
+    ALLOC(h->d_tmp_ll, sizeof(long long) * (size_t)(N + K_max + 2));
+#undef ALLOC
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    CU(cudaEventCreate(&h->ev2));
+    CU(cudaEventCreate(&h->ev3));
+    CU(cudaMemset(h->d_err, 0, sizeof(int)));
+    CU(cudaMemset(h->d_z, 0xff, sizeof(int) * (size_t)N));
+    CU(cudaMemset(h->d_counts, 0, sizeof(long long) * (K_max + 1)));
+    CU(cudaMemset(h->d_num, 0, sizeof(double) * (size_t)(K_max + 1) * DP));
+    CU(cudaMemset(h->d_S, 0, sizeof(double) * (size_t)(K_max + 1) * SS));
+    CU(cudaMemset(h->d_rec, 0, sizeof(double) * (size_t)(K_max + 1) * R));
+    std::vector<int> neg(K_max, -1), fr(K_max);
+    for (int t = 0; t < K_max; ++t) fr[t] = K_max - 1 - t;
+    CU(cudaMemcpy(h->d_slot_of_uid, neg.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_uid_of_slot, neg.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_uid_free, fr.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice));
+    Ctl c;
+    memset(&c, 0, sizeof(c));
+    c.n_free = K_max;
+    c.first = POS_INF;
+    c.first3[0][0] = c.first3[1][0] = c.first3[2][0] = (unsigned long long)POS_INF;
+    const double one = 1.0;
+    memcpy(&c.margin_bits, &one, 8);
+    CU(cudaMemcpy(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
+    h->K = 0;
+    return 0;
 }
 
 static int check_dev_err(bgmm_handle *h, const char *what) {
@@ -399,8 +460,8 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
     h->smem_item = fixed + 32;
     h->smem_optin = smem_max;
     if (int rc = prep(h)) { delete h; return rc; }
-    if (int rc = h->ops->fast_setup(h)) { free_all(h); delete h; return rc; }
-
+    h->sb = new SharedBufs();
+    SharedBufs *b = h->sb;
 #define ALLOC(ptr, bytes)                                                                             \
     do {                                                                                              \
         cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                                        \
@@ -409,32 +470,17 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
             return fail(BGMM_ENOMEM, std::string("cudaMalloc ") + #ptr + ": " + cudaGetErrorString(e_)); \
         }                                                                                             \
     } while (0)
-    ALLOC(h->dX, sizeof(double) * (size_t)N * DP);
-    ALLOC(h->d_log_prior, sizeof(double) * (size_t)N);
-    ALLOC(h->d_lgam, sizeof(double) * (size_t)need);
-    ALLOC(h->d_logv, sizeof(double) * (size_t)need);
-    ALLOC(h->d_m0, sizeof(double) * DP);
-    ALLOC(h->d_S0, sizeof(double) * SS);
-    ALLOC(h->d_z, sizeof(int) * (size_t)N);
-    ALLOC(h->d_slot_of_uid, sizeof(int) * K_max);
-    ALLOC(h->d_uid_of_slot, sizeof(int) * K_max);
-    ALLOC(h->d_uid_free, sizeof(int) * K_max);
-    ALLOC(h->d_counts, sizeof(long long) * (K_max + 1));
-    ALLOC(h->d_num, sizeof(double) * (size_t)(K_max + 1) * DP);
-    ALLOC(h->d_S, sizeof(double) * (size_t)(K_max + 1) * SS);
-    ALLOC(h->d_rec, sizeof(double) * (size_t)(K_max + 1) * R);
-    ALLOC(h->d_wbuf, sizeof(double) * (size_t)h->grid * (K_max + 1) * T_SWEEP);
-    ALLOC(h->d_rec_prior, sizeof(double) * R);
-    ALLOC(h->d_ctl, sizeof(Ctl));
-    ALLOC(h->d_err, sizeof(int));
-    ALLOC(h->d_u, sizeof(double) * (size_t)N);
-    ALLOC(h->d_order, sizeof(long long) * (size_t)N);
-    ALLOC(h->d_tmp_ll, sizeof(long long) * (size_t)(N + K_max + 2));
+    ALLOC(b->dX, sizeof(double) * (size_t)N * DP);
+    ALLOC(b->d_log_prior, sizeof(double) * (size_t)N);
+    ALLOC(b->d_lgam, sizeof(double) * (size_t)need);
+    ALLOC(b->d_logv, sizeof(double) * (size_t)need);
+    ALLOC(b->d_m0, sizeof(double) * DP);
+    ALLOC(b->d_S0, sizeof(double) * SS);
 #undef ALLOC
-    CU(cudaEventCreate(&h->ev0));
-    CU(cudaEventCreate(&h->ev1));
-    CU(cudaEventCreate(&h->ev2));
-    CU(cudaEventCreate(&h->ev3));
+    h->dX = b->dX; h->d_log_prior = b->d_log_prior; h->d_lgam = b->d_lgam; h->d_logv = b->d_logv;
+    h->d_m0 = b->d_m0; h->d_S0 = b->d_S0;
+    if (int rc = h->ops->fast_setup(h)) { free_all(h); delete h; return rc; }
+    if (int rc = alloc_chain_state(h)) { free_all(h); delete h; return rc; }
 
     // uploads
     if (DP == D) {
@@ -459,32 +505,34 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
     }
     CU(cudaMemcpy(h->d_m0, h->m0.data(), sizeof(double) * DP, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_S0, h->S0p.data(), sizeof(double) * SS, cudaMemcpyHostToDevice));
-    CU(cudaMemset(h->d_err, 0, sizeof(int)));
-    CU(cudaMemset(h->d_z, 0xff, sizeof(int) * (size_t)N));
-    CU(cudaMemset(h->d_counts, 0, sizeof(long long) * (K_max + 1)));
-    CU(cudaMemset(h->d_num, 0, sizeof(double) * (size_t)(K_max + 1) * DP));
-    CU(cudaMemset(h->d_S, 0, sizeof(double) * (size_t)(K_max + 1) * SS));
-    CU(cudaMemset(h->d_rec, 0, sizeof(double) * (size_t)(K_max + 1) * R));
-    {
-        std::vector<int> neg(K_max, -1), fr(K_max);
-        for (int t = 0; t < K_max; ++t) fr[t] = K_max - 1 - t;
-        CU(cudaMemcpy(h->d_slot_of_uid, neg.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(h->d_uid_of_slot, neg.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(h->d_uid_free, fr.data(), sizeof(int) * K_max, cudaMemcpyHostToDevice));
-        Ctl c;
-        memset(&c, 0, sizeof(c));
-        c.n_free = K_max;
-        c.first = POS_INF;
-        c.first3[0][0] = c.first3[1][0] = c.first3[2][0] = (unsigned long long)POS_INF;
-        const double one = 1.0;
-        memcpy(&c.margin_bits, &one, 8);
-        CU(cudaMemcpy(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
-    }
-    h->K = 0;
     // cached_log_prior
     Params p = make_params(h);
     if (int rc = h->ops->log_prior(h, p)) { free_all(h); delete h; return rc; }
     if (int rc = check_dev_err(h, "log_prior")) { free_all(h); delete h; return rc; }
+    *out = h;
+    return 0;
+}
+
+int bgmm_fork(bgmm_t *parent, bgmm_t **out) {
+    if (!parent || !out) return fail(BGMM_EINVAL, "NULL argument");
+    *out = nullptr;
+    CU(cudaSetDevice(parent->device));
+    bgmm_handle *h = new bgmm_handle();
+    h->device = parent->device; h->stream = parent->stream;
+    h->N = parent->N; h->D = parent->D; h->DP = parent->DP; h->cov = parent->cov; h->K_max = parent->K_max; h->Kc = parent->Kc;
+    h->k0 = parent->k0; h->v0 = parent->v0; h->m0 = parent->m0; h->S0p = parent->S0p; h->logdet_S0 = parent->logdet_S0;
+    h->num_sms = parent->num_sms; h->grid = parent->grid; h->smem_bytes = parent->smem_bytes;
+    h->smem_item = parent->smem_item; h->smem_optin = parent->smem_optin; h->ops = parent->ops;
+    h->guard = parent->guard; h->watchdog_ns = parent->watchdog_ns; h->engine = parent->engine;
+    h->sb = parent->sb;
+    h->sb->refs += 1;
+    SharedBufs *b = h->sb;
+    h->dX = b->dX; h->d_log_prior = b->d_log_prior; h->d_lgam = b->d_lgam; h->d_logv = b->d_logv;
+    h->d_m0 = b->d_m0; h->d_S0 = b->d_S0;
+    if (int rc = h->ops->fast_setup(h)) { free_all(h); delete h; return rc; }
+    if (int rc = alloc_chain_state(h)) { free_all(h); delete h; return rc; }
+    // the prior's generic record (bgmm_log_prior's source) is per handle: copy the parent's
+    CU(cudaMemcpy(h->d_rec_prior, parent->d_rec_prior, sizeof(double) * h->ops->rec_len, cudaMemcpyDeviceToDevice));
     *out = h;
     return 0;
 }
@@ -674,6 +722,11 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     const bool ran_fast = fast || generic_from >= 0;
     if (!fast) {
         p.start_pos = generic_from < 0 ? 0 : generic_from;
+        if (!h->d_wbuf) {   // the generic engine's window scratch, on first use
+            cudaError_t e_ = cudaMalloc((void **)&h->d_wbuf, sizeof(double) * (size_t)h->grid * (h->K_max + 1) * T_SWEEP);
+            if (e_ != cudaSuccess) return fail(BGMM_ENOMEM, std::string("cudaMalloc d_wbuf: ") + cudaGetErrorString(e_));
+        }
+        p.wbuf = h->d_wbuf;
         if (!ran_fast) CU(cudaEventRecord(h->ev2, st));
         if (int rc = h->ops->sweep(h, p)) return rc;
         if (!ran_fast) CU(cudaEventRecord(h->ev3, st));
@@ -711,6 +764,140 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     // the records the auxiliary entry points use were rebuilt after the sweep: report a failure of that rebuild now,
     // not from whichever call happens to look next
     return check_dev_err(h, "sweep (records after the sweep)");
+}
+
+// ---------------------------------------------------------------------------------------------
+// bgmm_sweep_many: one sweep of n independent chains with ONE kernel launch, one CTA per chain (the register-resident
+// sequential engine with the CTA as the chain's only replica).  Burn-in is a serial chain per datum: a single chain
+// keeps one SM busy, so the GPU's other SMs run other chains (BASELINE.json configs[3] is 8 chains).
+// ---------------------------------------------------------------------------------------------
+int bgmm_sweep_many(bgmm_t *const *hs, int32_t n, const int64_t *const *d_orders, const double *const *d_uniforms,
+                    double alpha, double power, bgmm_sweep_stats *out) {
+    if (!hs || n < 1) return fail(BGMM_EINVAL, "no chains");
+    if (!(alpha > 0.0) || !(power > 0.0)) return fail(BGMM_EINVAL, "alpha and power must be > 0");
+    bgmm_handle *h0 = hs[0];
+    if (!h0) return fail(BGMM_EINVAL, "handle is NULL");
+    for (int c = 0; c < n; ++c) {
+        bgmm_handle *h = hs[c];
+        if (!h) return fail(BGMM_EINVAL, "handle is NULL");
+        if (h->device != h0->device || h->stream != h0->stream || h->DP != h0->DP || h->cov != h0->cov ||
+            h->K_max != h0->K_max || h->ops != h0->ops)
+            return fail(BGMM_EINVAL, "the chains of one bgmm_sweep_many call must share device, stream, D, covariance type and K_max");
+        if (!h->fast_ok) return fail(BGMM_EINVAL, "bgmm_sweep_many needs the resident engine (full covariance, D <= 16)");
+        for (int d = 0; d < c; ++d) if (hs[d] == h) return fail(BGMM_EINVAL, "a chain appears twice");
+    }
+    CU(cudaSetDevice(h0->device));
+    cudaStream_t st = h0->stream;
+    if (h0->pv_cap < n) {
+        cudaFree(h0->d_pv);
+        h0->d_pv = nullptr;
+        h0->pv_cap = 0;
+        CU(cudaMalloc((void **)&h0->d_pv, sizeof(Params) * (size_t)n));
+        h0->pv_cap = n;
+    }
+    std::vector<Params> pv(n);
+    std::vector<Ctl> ctl(n);
+    for (int c = 0; c < n; ++c) CU(cudaMemcpyAsync(&ctl[c], hs[c]->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const double one = 1.0;
+    for (int c = 0; c < n; ++c) {
+        bgmm_handle *h = hs[c];
+        h->launches = 0;
+        const long long *d_order = d_orders ? (const long long *)d_orders[c] : nullptr;
+        const double *d_u = d_uniforms ? d_uniforms[c] : nullptr;
+        if (!d_u) {
+            const int T = 256;
+            k_philox<<<(unsigned)((h->N + T - 1) / T), T, 0, st>>>(h->d_u, h->N, h->seed, (unsigned long long)h->sweep_index);
+            CU(cudaGetLastError());
+            h->launches += 1;
+            d_u = h->d_u;
+        }
+        Ctl &k = ctl[c];
+        if (k.K > h->Kcap) return fail(BGMM_EINVAL, "a chain has more live components than the resident engine holds; sweep it with bgmm_sweep");
+        k.moves = k.births = k.deaths = k.evals = k.windows = k.seq_data = k.wasted = 0;
+        k.explicit_evals = k.refreshes = k.guard_hits = k.fast_steps = 0;
+        k.watchdog_ns = h->watchdog_ns;
+        memset(k.prof, 0, sizeof(k.prof));
+        memcpy(&k.margin_bits, &one, 8);
+        k.error = 0; k.bar_count = 0; k.rb_count = 0; k.rb_word = 0; k.pos = 0; k.win = 0; k.first = POS_INF; k.n_dirty = 0;
+        CU(cudaMemcpyAsync(h->d_ctl, &k, sizeof(Ctl), cudaMemcpyHostToDevice, st));
+        if (d_order) {
+            unsigned int *bits = (unsigned int *)h->d_tmp_ll;
+            CU(cudaMemsetAsync(bits, 0, sizeof(unsigned int) * (size_t)((h->N + 31) / 32), st));
+            const int T = 256;
+            k_check_perm<<<(unsigned)((h->N + T - 1) / T), T, 0, st>>>(d_order, h->N, bits, h->d_err);
+            CU(cudaGetLastError());
+            h->launches += 1;
+        }
+        Params p = make_params(h);
+        p.order = d_order; p.u = d_u;
+        p.log_alpha = log(alpha); p.power = power;
+        p.init_gap = 0.0; p.engine = 1; p.solo = 1;
+        CU(cudaMemcpyAsync(h->d_z2, h->d_z, sizeof(int) * (size_t)h->N, cudaMemcpyDeviceToDevice, st));
+        if (int rc = h->ops->fast_prep(h, p, k.K)) return rc;
+        pv[c] = p;
+    }
+    for (int c = 0; c < n; ++c)
+        if (int rc = check_dev_err(hs[c], "sweep_many (scan order / record set-up)")) return rc;
+    CU(cudaMemcpyAsync(h0->d_pv, pv.data(), sizeof(Params) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(h0->ev2, st));
+    if (int rc = h0->ops->fast_sweep_many(h0, h0->d_pv, n)) return rc;
+    CU(cudaEventRecord(h0->ev3, st));
+    for (int c = 0; c < n; ++c) CU(cudaMemcpyAsync(&ctl[c], hs[c]->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    float ms_k = 0.f;
+    CU(cudaEventElapsedTime(&ms_k, h0->ev2, h0->ev3));
+    int first_rc = 0;
+    for (int c = 0; c < n; ++c) {
+        bgmm_handle *h = hs[c];
+        Ctl &k = ctl[c];
+        std::swap(h->d_z, h->d_z2);
+        Params p = pv[c];
+        p.z_uid = h->d_z; p.z_out = h->d_z2;
+        long long generic_from = -1;
+        if (k.K > 0) {
+            if (int rc = h->ops->refactor_all(h, p, 0, k.K)) return rc;
+            h->launches += 1;
+        }
+        if (k.error == fast::E_NEED_GENERIC) {
+            // more live components than the resident engine holds: this chain finishes its sweep on the generic engine
+            generic_from = k.pos;
+            k.error = 0; k.bar_count = 0;
+            CU(cudaMemcpyAsync(h->d_ctl, &k, sizeof(Ctl), cudaMemcpyHostToDevice, st));
+            if (!h->d_wbuf) {
+                cudaError_t e_ = cudaMalloc((void **)&h->d_wbuf, sizeof(double) * (size_t)h->grid * (h->K_max + 1) * T_SWEEP);
+                if (e_ != cudaSuccess) return fail(BGMM_ENOMEM, std::string("cudaMalloc d_wbuf: ") + cudaGetErrorString(e_));
+            }
+            p.wbuf = h->d_wbuf; p.solo = 0; p.engine = 0; p.start_pos = generic_from;
+            if (int rc = h->ops->sweep(h, p)) return rc;
+            h->launches += 1;
+            CU(cudaMemcpyAsync(&k, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        h->K = k.K;
+        h->sweep_index += 1;
+        h->last_gap = (double)h->N / (double)(k.moves + 1);
+        if (out) {
+            bgmm_sweep_stats &o = out[c];
+            memset(&o, 0, sizeof(o));
+            o.K = k.K; o.moves = k.moves; o.births = k.births; o.deaths = k.deaths; o.evals = k.evals;
+            o.windows = k.windows; o.seq_data = k.seq_data; o.wasted = k.wasted;
+            memcpy(&o.min_margin, &k.margin_bits, 8);
+            o.device_ms = ms_k; o.sweep_kernel_ms = ms_k;
+            o.explicit_evals = k.explicit_evals; o.refreshes = k.refreshes; o.generic_from = generic_from;
+            for (int t = 0; t < 16; ++t) o.phase_cycles[t] = k.prof[t];
+            o.launches = h->launches + (c == 0 ? 1 : 0);
+            o.guard_hits = k.guard_hits; o.fast_steps = k.fast_steps;
+        }
+        if (k.error != 0 && first_rc == 0)
+            first_rc = fail(k.error == BGMM_EKMAX ? BGMM_EKMAX : k.error,
+                            "sweep_many: chain " + std::to_string(c) + (k.error == BGMM_EKMAX
+                                ? ": a new component would exceed K_max" : ": non-finite weights or covariance not positive definite"));
+    }
+    if (first_rc) return first_rc;
+    for (int c = 0; c < n; ++c)
+        if (int rc = check_dev_err(hs[c], "sweep_many (records after the sweep)")) return rc;
+    return 0;
 }
 
 int bgmm_sweep_dev(bgmm_t *h, const int64_t *d_order, const double *d_uniforms, double alpha, double power,

@@ -37,7 +37,7 @@ constexpr int REFRESH_EVERY = 1024;   // rank-one updates of a record before it 
 constexpr int NB_MAX = 6;             // weights per lane in the draw: supports K + 1 <= 192
 constexpr int E_NEED_GENERIC = 1;     // internal: a birth would exceed the resident capacity -> generic engine
 // a window round costs about as much as two sequential steps, so windows pay from a gap of ~2 data between movers
-constexpr double GAP_TO_WIN = 2.5, GAP_TO_SEQ = 1.7;
+constexpr double GAP_TO_WIN = 2.5, GAP_TO_SEQ = 1.7;   // (general step; with the register step of bgmm_seq.cuh: Params::gap_to_win / gap_to_seq)
 constexpr int WIN_PASSES_MAX = 8;
 constexpr int BULK_PASSES_MAX = 4;     // passes of the thread-per-datum evaluator in one window
 constexpr int BULK_MIN_ROWS = TF / 2;   // windows of at least this many data per SM use it: a pass of the
@@ -126,9 +126,16 @@ template <int DP> struct Lay {
     static constexpr int WS = (KS + 1 + 3) & ~3;
 };
 
-// grid barrier with a watchdog: replicas that stopped agreeing would otherwise spin forever
-static __device__ __noinline__ void f_grid_barrier(Ctl *c) {
+// grid barrier with a watchdog: replicas that stopped agreeing would otherwise spin forever.  A solo chain (one CTA is
+// the chain's only replica, bgmm_sweep_many) needs only its own writes to be complete: CTA barrier + fence.
+static __device__ __noinline__ void f_grid_barrier(const Params &p) {
+    Ctl *c = p.ctl;
     __syncthreads();
+    if (p.solo) {
+        if (threadIdx.x == 0) __threadfence();
+        __syncthreads();
+        return;
+    }
     if (threadIdx.x == 0) {
         unsigned int gen = ld_acquire_u32(&c->bar_gen);
         __threadfence();
@@ -154,11 +161,12 @@ struct FSh {
     long long pos;
     double gap;
     long long moves, births, deaths, evals, windows, seq_data, wasted, explicit_evals, refreshes;
-    long long guard_hits, fast_steps;
+    long long guard_hits, fast_steps, seq_moves0;
     double last_mg;          // margin of the draw just made (f_step)
     unsigned long long margin_bits;
     // datum being resolved
     int k_new, need_explicit, explicit_done, refresh_a, refresh_b;
+    int rare_seq;   // bgmm_seq.cuh: step sequence number of a datum that must go through the general step
     // record version: bumped by every change of the records; the change from ver - 1 to ver touched only the
     // components logged in dlog_a / dlog_b (-1: none) unless it is <= dall_ver
     int ver, dall_ver;               // dall_ver: last version whose change was not confined to two components
@@ -241,10 +249,10 @@ template <int DP> __host__ __device__ inline size_t fast_smem_bytes(int K_max) {
     size_t d = (size_t)Ly::R * Ly::KS + 2 + 2 * (size_t)Ly::R + (size_t)(NWARP + 1) * Ly::WS + (size_t)NWARP * DP +
                (size_t)SEQ_BATCH * DP + 2 * SEQ_BATCH + SEQ_BATCH /*ib*/ + SEQ_BATCH / 2 /*uidb*/ + 4 * DP + 4 * NT_W +
                Ly::PP + DP * DP + DP + fm::TAB_LEN;
-    size_t b = d * sizeof(double);
+    size_t b = d * sizeof(double) + 16;
     b += 3 * (size_t)K_max * sizeof(int);
-    b += ((size_t)Ly::PP * sizeof(unsigned short) + 15) & ~(size_t)15;
-    b += sizeof(FSh) + 64;
+    b += (((size_t)Ly::PP + 7) & ~(size_t)7) * sizeof(unsigned short);
+    b += ((sizeof(FSh) + 15) & ~(size_t)15) + 64;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -270,15 +278,43 @@ template <int DP> __device__ inline FSmem<DP> fast_carve(double *base, const Par
     s.W = q; q += DP * DP;
     s.mm = q; q += DP;
     s.fm = q; q += fm::TAB_LEN;
-    int *t = (int *)q;
+    // the chain state block sits at a compile-time offset (SOff<DP>::SH); only the three tables behind it are
+    // sized at run time
+    q = (double *)(((uintptr_t)q + 15) & ~(uintptr_t)15);
+    s.sh = (FSh *)q;
+    unsigned short *r = (unsigned short *)((char *)q + ((sizeof(FSh) + 15) & ~(size_t)15));
+    s.rc = r; r += (Ly::PP + 7) & ~7;
+    int *t = (int *)r;
     s.slot_of_uid = t; t += p.K_max;
     s.uid_of_slot = t; t += p.K_max;
     s.uid_free = t; t += p.K_max;
-    unsigned short *r = (unsigned short *)t;
-    s.rc = r; r += Ly::PP;
-    s.sh = (FSh *)(((uintptr_t)r + 15) & ~(uintptr_t)15);
     return s;
 }
+
+// Compile-time offsets (in doubles, from the start of the dynamic shared array) of the regions fast_carve lays out in
+// front of the run-time sized tables: code on a latency-critical path addresses shared memory as smem_raw[OFF + ...]
+// (immediate offsets, no pointer registers).  fast_sweep_body checks them against fast_carve once per launch.
+template <int DP> struct SOff {
+    using Ly = Lay<DP>;
+    static constexpr int REC = 0;
+    static constexpr int PRIOR = ((Ly::R * Ly::KS) + 1) & ~1;
+    static constexpr int TMPREC = PRIOR + Ly::R;
+    static constexpr int EW = TMPREC + Ly::R;
+    static constexpr int XW = EW + (NWARP + 1) * Ly::WS;
+    static constexpr int XB = XW + NWARP * DP;
+    static constexpr int UB = XB + SEQ_BATCH * DP;
+    static constexpr int LPB = UB + SEQ_BATCH;
+    static constexpr int IB = LPB + SEQ_BATCH;
+    static constexpr int UIDB = IB + SEQ_BATCH;
+    static constexpr int DV = UIDB + SEQ_BATCH / 2;
+    static constexpr int VV = DV + 2 * DP;
+    static constexpr int NT = VV + 2 * DP;
+    static constexpr int A = NT + 4 * NT_W;
+    static constexpr int W = A + Ly::PP;
+    static constexpr int MM = W + DP * DP;
+    static constexpr int FM = MM + DP;
+    static constexpr int SH = (FM + fm::TAB_LEN + 1) & ~1;
+};
 
 // The FSmem pointers are generic (the struct is filled at run time), so loads through them are generic loads: they
 // go through the LSU's local/global path and wait on the long scoreboard.  On latency-critical single-warp paths the
@@ -736,8 +772,8 @@ __device__ __forceinline__ void red_add_f64(double *addr, double v) {
     asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
 template <int DP>
-__device__ __noinline__ void f_stats_axpy(const Params &p, const unsigned short *rc, int slot, const double *x, int sign,
-                                          int init_prior, int t, int nthr) {
+__device__ __forceinline__ void f_stats_axpy_inl(const Params &p, const unsigned short *rc, int slot, const double *x,
+                                                 int sign, int init_prior, int t, int nthr) {
     using Ly = Lay<DP>;
     const int D = p.D;
     double *S = p.S + (size_t)slot * Ly::PP;
@@ -773,6 +809,12 @@ __device__ __noinline__ void f_stats_axpy(const Params &p, const unsigned short 
     }
 }
 
+template <int DP>
+__device__ __noinline__ void f_stats_axpy(const Params &p, const unsigned short *rc, int slot, const double *x, int sign,
+                                          int init_prior, int t, int nthr) {
+    f_stats_axpy_inl<DP>(p, rc, slot, x, sign, init_prior, t, nthr);
+}
+
 // ---------------------------------------------------------------------------------------------
 // rare paths of a step, out of line
 // ---------------------------------------------------------------------------------------------
@@ -786,7 +828,7 @@ template <int DP> __device__ __noinline__ void f_delete_component(const Params &
     __syncthreads();
     if (k_old != L) {
         for (int e = tid; e < Ly::R; e += TF) s.rec[(size_t)e * ST + k_old] = s.rec[(size_t)e * ST + L];
-        if (blockIdx.x == 0) {
+        if (p.writer) {
             for (int e = tid; e < Ly::PP; e += TF)
                 __stcg(p.S + (size_t)k_old * Ly::PP + e, __ldcg(p.S + (size_t)L * Ly::PP + e));
             for (int e = tid; e < DP; e += TF) __stcg(p.num + (size_t)k_old * DP + e, __ldcg(p.num + (size_t)L * DP + e));
@@ -819,7 +861,7 @@ __device__ __noinline__ void f_explicit_own(const Params &p, const FSmem<DP> &s,
     using Ly = Lay<DP>;
     FSh &sh = *s.sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    f_grid_barrier(p.ctl);
+    f_grid_barrier(p);
     if (warp == 0) {
         const bool okf = f_exact_record_warp<DP>(p, 0, p.num + (size_t)k_old * DP, p.S + (size_t)k_old * Ly::PP,
                                                  n_old - 1.0, xs, s.rc, s.A, s.W, s.mm, s.tmprec, 1);
@@ -833,7 +875,7 @@ __device__ __noinline__ void f_explicit_own(const Params &p, const FSmem<DP> &s,
             }
         }
     }
-    f_grid_barrier(p.ctl);
+    f_grid_barrier(p);
 }
 
 // the weights' spread overflowed the exp scale of the fast draw: redo the datum in the log domain
@@ -901,7 +943,7 @@ __device__ __noinline__ void f_exact_redo(const Params &p, const FSmem<DP> &s, i
     constexpr int ST = Ly::KS;
     FSh &sh = *s.sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    f_grid_barrier(p.ctl);   // CTA 0's statistics are complete and stay frozen until the second barrier
+    f_grid_barrier(p);   // CTA 0's statistics are complete and stay frozen until the second barrier
     if (warp == 0) {
         bool okf = true;
         for (int k = 0; k < K && okf; ++k) {
@@ -921,7 +963,7 @@ __device__ __noinline__ void f_exact_redo(const Params &p, const FSmem<DP> &s, i
             sh.dall_ver = sh.ver;
         }
     }
-    f_grid_barrier(p.ctl);
+    f_grid_barrier(p);
     if (sh.error) return;
     if (tid < K) {
         ew[tid] = ((own_live && tid == k_old) ? f_weight_exact<DP, 1>(s.tmprec, xs) : f_weight_exact<DP, ST>(s.rec + tid, xs)) -
@@ -956,7 +998,7 @@ __device__ __noinline__ void f_refresh(const Params &p, const FSmem<DP> &s, int 
     using Ly = Lay<DP>;
     FSh &sh = *s.sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    f_grid_barrier(p.ctl);
+    f_grid_barrier(p);
     if (warp == 0) {
         bool okf = true;
         int cnt = 0;
@@ -975,7 +1017,7 @@ __device__ __noinline__ void f_refresh(const Params &p, const FSmem<DP> &s, int 
             sh.refreshes += cnt;
         }
     }
-    f_grid_barrier(p.ctl);
+    f_grid_barrier(p);
 }
 
 // a new component opens in slot K, initialised with the prior (gaussian_components.py:161-164).  false: error set
@@ -1035,7 +1077,7 @@ __device__ __noinline__ void f_move_phase(const Params &p, const FSmem<DP> &s, i
             sh.dlog_b[v & (DLOG - 1)] = k_new;
             if (died || expl) sh.dall_ver = v;
         }
-    } else if (blockIdx.x == 0 && warp >= 8) {
+    } else if (p.writer && warp >= 8) {
         // CTA 0: the bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition)
         if (warp < 12) {
             if (remove_now) f_stats_axpy<DP>(p, s.rc, k_old, xs, -1, 0, tid - 256, 128);
@@ -1608,11 +1650,17 @@ __device__ __forceinline__ long long f_next_window(double gap, long long pos, lo
     return left < (long long)win ? left : (long long)win;
 }
 
+}  // namespace fast
+}  // namespace bgmm
+#include "bgmm_seq.cuh"
+namespace bgmm {
+namespace fast {
+
 // ---------------------------------------------------------------------------------------------
-// the sweep kernel: cooperative grid, one CTA per SM
+// the sweep kernel: cooperative grid, one CTA per SM -- or, for bgmm_sweep_many, one CTA per chain (solo)
 // ---------------------------------------------------------------------------------------------
 template <int DP>
-__global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
+__device__ __forceinline__ void fast_sweep_body(const Params &p_in) {
     extern __shared__ __align__(16) double smem_raw[];
     using Ly = Lay<DP>;
     constexpr int ST = Ly::KS;
@@ -1620,14 +1668,31 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
     // in local memory
     __shared__ Params p_sh;
     __shared__ FSmem<DP> s_sh;
-    if (threadIdx.x == 0) { p_sh = p_in; s_sh = fast_carve<DP>(smem_raw, p_in); }
+    if (threadIdx.x == 0) {
+        p_sh = p_in;
+        p_sh.writer = (p_in.solo || blockIdx.x == 0) ? 1 : 0;
+        s_sh = fast_carve<DP>(smem_raw, p_in);
+    }
     __syncthreads();
     const Params &p = p_sh;
     const FSmem<DP> &s = s_sh;
     FSh &sh = *s.sh;
     Ctl *ctl = p.ctl;
     const int tid = threadIdx.x;
-    const bool cta0 = (blockIdx.x == 0);
+    const bool cta0 = (p.writer != 0);
+    {
+        using O = SOff<DP>;
+        const bool ok = s.prior == smem_raw + O::PRIOR && s.tmprec == smem_raw + O::TMPREC && s.ew == smem_raw + O::EW &&
+                        s.xw == smem_raw + O::XW && s.xb == smem_raw + O::XB && s.ub == smem_raw + O::UB &&
+                        s.lpb == smem_raw + O::LPB && (double *)s.ib == smem_raw + O::IB &&
+                        (double *)s.uidb == smem_raw + O::UIDB && s.dv == smem_raw + O::DV && s.vv == smem_raw + O::VV &&
+                        s.nt == smem_raw + O::NT && s.A == smem_raw + O::A && s.W == smem_raw + O::W &&
+                        s.mm == smem_raw + O::MM && s.fm == smem_raw + O::FM && (double *)s.sh == smem_raw + O::SH;
+        if (!ok) {   // fast_carve and SOff disagree: a build error, reported instead of silently corrupting memory
+            if (tid == 0 && cta0) __stcg(&ctl->error, -7);
+            return;
+        }
+    }
 
     // ---- prologue: replicate the chain state ----
     if (tid == 0) {
@@ -1644,11 +1709,13 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
         sh.margin_bits = (unsigned long long)__double_as_longlong(one);
         sh.round = 0;
         sh.k_new = 0; sh.need_explicit = 0; sh.explicit_done = 0; sh.refresh_a = 0; sh.refresh_b = 0;
+        sh.rare_seq = 0;
         sh.ver = 1; sh.dall_ver = 1;
         for (int t = 0; t < DLOG; ++t) sh.dlog_a[t] = sh.dlog_b[t] = -1;
         for (int t = 0; t < PH_COUNT; ++t) sh.prof[t] = 0;
         sh.prof_last = clock64();
-        sh.mode = (p.engine == 2) ? 1 : ((p.engine == 1) ? 0 : (p.init_gap >= GAP_TO_WIN ? 1 : 0));
+        sh.mode = (p.engine == 2) ? 1 : ((p.engine == 1) ? 0 : (p.init_gap >= (double)p.gap_to_win ? 1 : 0));
+        if (p.solo) sh.mode = 0;
         sh.win = f_next_window(p.init_gap, p.start_pos, p.N, p.win_factor);
         const uint32_t mb = smem_u32(&sh.mbar);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
@@ -1699,7 +1766,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
         }
     }
     // no replica may still be reading the initial state when CTA 0 starts changing it
-    f_grid_barrier(ctl);
+    f_grid_barrier(p);
 
     WCache cache;
     cache.nj = (long long)blockIdx.x + (long long)gridDim.x * (tid >> 5);
@@ -1714,7 +1781,13 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
         const long long pos = sh.pos;
         if (pos >= p.N || sh.error != 0) break;
         const int mode = sh.mode;
-        if (mode == 0) {
+        if (mode == 0 && sh.K < SEQ_KMAX && !(p.tune & 8)) {
+            // dense movers: the register-resident sequential step (bgmm_seq.cuh); runs batches until the engine should
+            // change mode, K outgrows its layout, or the sweep ends
+            __syncthreads();
+            seq = f_seq_run<DP>(p, s, seq);
+            cache.j = -1; cache.stage = 0;   // its staging reuses nothing of the evaluators', but their rows are void
+        } else if (mode == 0) {
             const int nb = (int)min((long long)SEQ_BATCH, p.N - pos);
             const long long moves0 = sh.moves;
             __syncthreads();
@@ -1726,7 +1799,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
                 sh.seq_data += done;
                 sh.pos = pos + done;
                 sh.dall_ver = sh.ver;   // several changes since the evaluators last looked
-                if (p.engine == 0 && sh.gap >= GAP_TO_WIN) sh.mode = 1;
+                if (p.engine == 0 && sh.gap >= (double)p.gap_to_win) sh.mode = 1;
                 sh.win = f_next_window(sh.gap, sh.pos, p.N, p.win_factor);
             }
         } else {
@@ -1796,7 +1869,7 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             if (tid == 0) {
                 sh.windows += 1;
                 sh.round = r + 1u;
-                if (p.engine == 0 && sh.gap < GAP_TO_SEQ) sh.mode = 0;
+                if (p.engine == 0 && sh.gap < (double)p.gap_to_seq) sh.mode = 0;
                 sh.win = f_next_window(sh.gap, sh.pos, p.N, p.win_factor);
             }
         }
@@ -1838,6 +1911,17 @@ __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) {
             for (int t = 0; t < PH_COUNT; ++t) __stcg(&ctl->prof[t], sh.prof[t]);
         }
     }
+}
+
+template <int DP> __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) { fast_sweep_body<DP>(p_in); }
+
+// bgmm_sweep_many: CTA c advances chain c (its Params at pv[c]) on its own -- the sequential engine with the CTA as the
+// chain's only replica; chains beyond the number of resident CTAs simply queue (there is no inter-CTA dependency)
+template <int DP> __global__ void __launch_bounds__(TF, 1) k_fast_sweep_many(const Params *__restrict__ pv) {
+    __shared__ Params p_mine;
+    if (threadIdx.x == 0) p_mine = pv[blockIdx.x];
+    __syncthreads();
+    fast_sweep_body<DP>(p_mine);
 }
 
 // records of all live components (and the prior) in the engine's format, from the bit-exact statistics.

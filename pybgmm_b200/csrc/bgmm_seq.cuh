@@ -1,0 +1,471 @@
+// bgmm_seq.cuh -- the register-resident sequential step of the B200 sweep engine (dense movers: cold chains, D = 2).
+//
+// Semantics: the per-datum loop of CRPMM / PCRPMM.collapsed_gibbs_sampler (igmm/crpmm.py:57-88, igmm/pcrpmm.py:93-131),
+// one datum after the other, exactly as bgmm_fast.cuh's f_step resolves it -- this file is the common case of that step
+// (a datum that stays, or moves between two live components) made short; everything else (a component dies, a birth,
+// an unassigned datum, an untrusted closed form, overflow, a draw inside the margin guard, drift refresh) is handed to
+// f_step unchanged.
+//
+// Why it exists: when most data move, the chain is one serial step per datum and the step's latency is the whole
+// story.  f_step streams every live record through shared memory for every datum (K x 1.2 KB at D = 16: the 128 B/clk
+// shared-memory port alone is ~1.4 k cycles per datum) and chains five CTA barriers through out-of-line phases.  Here
+//   * the matrices B_k = S_N^-1 of all live components live in REGISTERS for the whole run: thread (k, part) of the
+//     CTA owns one of four blocks of B_k -- the two diagonal triangles LL / HH and the two row-halves of the
+//     off-diagonal block (D = 16: 36 / 36 / 32 / 32 doubles, 72 of the thread's 128 registers); `part` is warp-uniform
+//     (warps 4 part .. 4 part + 3), lanes run over components: no divergence, and an evaluation reads only the mean
+//     and x from shared memory (8-12 doubles per thread instead of 44);
+//   * a datum that stays costs three barriers (partial sums, scan of the 4 x 32 choices, draw); a move adds two:
+//     the four owners of each of the two touched components rebuild v = B d from their blocks (partial products
+//     meet in shared memory), then update their registers (Sherman-Morrison, gaussian_components.py:161-166 /
+//     :184-185 as a rank-one change of S_N), the mean and the scalars; no thread outside those eight does anything;
+//   * the bit-exact statistics are updated by the writer CTA with L2 reductions, off the critical path, as before.
+// The quadratic form is summed in the same order as f_quad_part16, so at D = 16 the weights are bit-identical to
+// f_step's and handing a datum over never changes its draw.  Registers are written back to the shared-memory records
+// whenever anything else needs them (rare paths, window mode, the end of the sweep).
+#pragma once
+
+namespace bgmm {
+namespace fast {
+
+constexpr int SEQ_KMAX = 128;   // the K + 1 choices sit one per thread in warps 0..3
+
+// geometry of block PART of the symmetric DP x DP matrix B (packed lower triangle, row-major: e = a (a + 1) / 2 + b)
+//   L = [0, H), U = [H, DP);  part 0: triangle LL, part 1: triangle UU, part 2 / 3: rows [R0, R0 + RN) of the block UL
+template <int DP, int PART> struct Blk {
+    static constexpr int H = (DP + 1) / 2;
+    static constexpr int NU = DP - H;
+    static constexpr int R2 = (NU + 1) / 2;
+    static constexpr bool TRI = PART <= 1;
+    static constexpr int O = PART == 0 ? 0 : H;            // TRI: first row / column
+    static constexpr int TN = PART == 0 ? H : NU;          // TRI: size
+    static constexpr int R0 = PART == 2 ? H : H + R2;      // RECT: first row
+    static constexpr int RN = PART == 2 ? R2 : NU - R2;    // RECT: rows (columns are L)
+    static constexpr int NE = TRI ? TN * (TN + 1) / 2 : RN * H;
+    static constexpr int NEA = NE > 0 ? NE : 1;
+    static constexpr int TNA = TN > 0 ? TN : 1;
+    static constexpr int RNA = RN > 0 ? RN : 1;
+};
+
+__device__ __forceinline__ void bar_sync_all() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_front() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // warps 0..3
+
+// registers <-> shared-memory records (element-major rec[e * ST + k])
+template <int DP, int PART, int ST>
+__device__ __forceinline__ void seq_load_block(const double *__restrict__ col, double (&B)[Blk<DP, PART>::NEA]) {
+    using G = Blk<DP, PART>;
+    if constexpr (G::TRI) {
+#pragma unroll
+        for (int a = 0; a < G::TN; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) B[a * (a + 1) / 2 + b] = col[((G::O + a) * (G::O + a + 1) / 2 + G::O + b) * ST];
+    } else {
+#pragma unroll
+        for (int a = 0; a < G::RN; ++a)
+#pragma unroll
+            for (int b = 0; b < G::H; ++b) B[a * G::H + b] = col[((G::R0 + a) * (G::R0 + a + 1) / 2 + b) * ST];
+    }
+}
+template <int DP, int PART, int ST>
+__device__ __forceinline__ void seq_store_block(double *__restrict__ col, const double (&B)[Blk<DP, PART>::NEA]) {
+    using G = Blk<DP, PART>;
+    if constexpr (G::TRI) {
+#pragma unroll
+        for (int a = 0; a < G::TN; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) col[((G::O + a) * (G::O + a + 1) / 2 + G::O + b) * ST] = B[a * (a + 1) / 2 + b];
+    } else {
+#pragma unroll
+        for (int a = 0; a < G::RN; ++a)
+#pragma unroll
+            for (int b = 0; b < G::H; ++b) col[((G::R0 + a) * (G::R0 + a + 1) / 2 + b) * ST] = B[a * G::H + b];
+    }
+}
+
+// this block's share of  sum_a d_a (sum_{b<a} B_ab d_b + B_aa d_a / 2),  d = m - x;  q = 2 * (sum over the four parts).
+// Same operation order as f_quad_part16.
+template <int DP, int PART, int ST>
+__device__ __forceinline__ double seq_quad_part(const double (&B)[Blk<DP, PART>::NEA], const double *__restrict__ mu,
+                                                const double *__restrict__ x) {
+    using G = Blk<DP, PART>;
+    double q = 0.0;
+    if constexpr (G::TRI) {
+        double d[G::TNA];
+#pragma unroll
+        for (int a = 0; a < G::TN; ++a) d[a] = mu[(G::O + a) * ST] - x[G::O + a];
+#pragma unroll
+        for (int a = 0; a < G::TN; ++a) {
+            double r = 0.0;
+#pragma unroll
+            for (int b = 0; b < a; ++b) r = fma(B[a * (a + 1) / 2 + b], d[b], r);
+            r = fma(0.5 * B[a * (a + 1) / 2 + a], d[a], r);
+            q = fma(d[a], r, q);
+        }
+    } else {
+        double dl[G::H], dh[G::RNA];
+#pragma unroll
+        for (int b = 0; b < G::H; ++b) dl[b] = mu[b * ST] - x[b];
+#pragma unroll
+        for (int a = 0; a < G::RN; ++a) dh[a] = mu[(G::R0 + a) * ST] - x[G::R0 + a];
+#pragma unroll
+        for (int a = 0; a < G::RN; ++a) {
+            double r = 0.0;
+#pragma unroll
+            for (int b = 0; b < G::H; ++b) r = fma(B[a * G::H + b], dl[b], r);
+            q = fma(dh[a], r, q);
+        }
+    }
+    return q;
+}
+
+// this block's share of v = B d (d = m - x), into the three partial-product slots vp[slot * DP + a]:
+//   slot 0: LL -> [0, H), UU -> [H, DP);  slot 1: part 2 -> [0, H) and its rows, part 3 -> its rows;
+//   slot 2: part 3 -> [0, H).  v_a = (slot0 + slot1) + slot2 (slot 2 only for a < H).  Empty blocks write zeros.
+template <int DP, int PART, int ST>
+__device__ __forceinline__ void seq_partial_v(const double (&B)[Blk<DP, PART>::NEA], const double *__restrict__ mu,
+                                              const double *__restrict__ x, double *__restrict__ vp) {
+    using G = Blk<DP, PART>;
+    if constexpr (G::TRI) {
+        double dkeep[G::TNA];
+#pragma unroll
+        for (int a = 0; a < G::TN; ++a) dkeep[a] = mu[(G::O + a) * ST] - x[G::O + a];
+#pragma unroll
+        for (int a = 0; a < G::TN; ++a) {
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b < G::TN; ++b) {
+                const int e = (a >= b) ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a;
+                acc = fma(B[e], dkeep[b], acc);
+            }
+            vp[G::O + a] = acc;
+        }
+    } else {
+        double dl[G::H], dh[G::RNA];
+#pragma unroll
+        for (int b = 0; b < G::H; ++b) dl[b] = mu[b * ST] - x[b];
+#pragma unroll
+        for (int a = 0; a < G::RN; ++a) dh[a] = mu[(G::R0 + a) * ST] - x[G::R0 + a];
+#pragma unroll
+        for (int a = 0; a < G::RN; ++a) {
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b < G::H; ++b) acc = fma(B[a * G::H + b], dl[b], acc);
+            vp[DP + G::R0 + a] = acc;
+        }
+#pragma unroll
+        for (int b = 0; b < G::H; ++b) {
+            double acc = 0.0;
+#pragma unroll
+            for (int a = 0; a < G::RN; ++a) acc = fma(B[a * G::H + b], dh[a], acc);
+            vp[(PART == 2 ? DP : 2 * DP) + b] = acc;
+        }
+    }
+}
+
+// B += gam v v^T on this block, v combined from the partial-product slots
+template <int DP, int PART>
+__device__ __forceinline__ void seq_rank_one(double (&B)[Blk<DP, PART>::NEA], const double *__restrict__ vp, double gam) {
+    using G = Blk<DP, PART>;
+    auto vat = [&](int a) -> double {
+        const double t = vp[a] + vp[DP + a];
+        return (a < G::H) ? t + vp[2 * DP + a] : t;
+    };
+    if constexpr (G::TRI) {
+        double v[G::TNA];
+#pragma unroll
+        for (int a = 0; a < G::TN; ++a) v[a] = vat(G::O + a);
+#pragma unroll
+        for (int a = 0; a < G::TN; ++a) {
+            const double ga = gam * v[a];
+#pragma unroll
+            for (int b = 0; b <= a; ++b) B[a * (a + 1) / 2 + b] = fma(ga, v[b], B[a * (a + 1) / 2 + b]);
+        }
+    } else {
+        double vl[G::H], vh[G::RNA];
+#pragma unroll
+        for (int b = 0; b < G::H; ++b) vl[b] = vat(b);
+#pragma unroll
+        for (int a = 0; a < G::RN; ++a) vh[a] = vat(G::R0 + a);
+#pragma unroll
+        for (int a = 0; a < G::RN; ++a) {
+            const double ga = gam * vh[a];
+#pragma unroll
+            for (int b = 0; b < G::H; ++b) B[a * G::H + b] = fma(ga, vl[b], B[a * G::H + b]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sequential batches with the B blocks in registers, for the warps of part PART.  Every warp of the CTA calls its own
+// instantiation; all take the same (CTA-uniform) decisions and meet at the same barriers.  Returns when the sweep is
+// over, on error, when the engine should go to windows, or when K outgrows the one-choice-per-thread layout.
+// ---------------------------------------------------------------------------------------------
+template <int DP, int PART>
+__device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int seq) {
+    using Ly = Lay<DP>;
+    using G = Blk<DP, PART>;
+    constexpr int ST = Ly::KS;
+    extern __shared__ __align__(16) double smem_raw[];
+    // everything on the step's path is addressed as smem_raw[compile-time offset + ...]: immediate offsets, no pointer
+    // registers next to the 72 that hold the B block
+    using O = SOff<DP>;
+    double *rec = smem_raw;
+    FSh &sh = *reinterpret_cast<FSh *>(smem_raw + O::SH);
+    const double *xb = smem_raw + O::XB;
+    const double *ub = smem_raw + O::UB, *lpb = smem_raw + O::LPB;
+    const long long *ib = reinterpret_cast<const long long *>(smem_raw + O::IB);
+    double *psum = smem_raw + O::A;                          // A and W are contiguous: 3 x 128 partial sums
+    double *qv = smem_raw + O::EW + NWARP * Ly::WS;          // f_step's row: the quadratic forms of this datum
+    double *vpb = smem_raw + O::DV;                          // dv, vv, nt are contiguous: 2 x 3 x DP partial products
+    double *ntb = qv + SEQ_KMAX;                             // 2 x 8 count-table entries (cp.async targets, 16-B aligned)
+    double *gdb = ntb + 16;                                  // (gam, den) of the two rank-one updates
+    int *kob = reinterpret_cast<int *>(smem_raw + O::MM);    // slot of the staged data's own components
+    const double *fmtab = smem_raw + O::FM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = tid & (SEQ_KMAX - 1);
+    double *col = rec + k;
+    const double *mu = col + Ly::MU * ST;
+    double *sc = col + Ly::SC * ST;
+
+    double B[G::NEA];
+    B[0] = 0.0;
+    seq_load_block<DP, PART, ST>(col, B);
+
+    while (true) {
+        const long long pos = sh.pos;
+        if (pos >= p.N || sh.error != 0 || sh.mode != 0 || sh.K >= SEQ_KMAX) break;
+        const int nb = (int)min((long long)SEQ_BATCH, p.N - pos);
+        if (tid == 0) sh.seq_moves0 = sh.moves;
+        bar_sync_all();   // everyone has read the loop state before thread 0 changes it again
+        // ---- stage the batch (as f_run) ----
+        for (int t = tid; t < nb * DP; t += TF) {
+            const int jj = t / DP, a = t % DP;
+            const long long j = pos + jj;
+            const long long i = p.order ? p.order[j] : j;
+            s.xb[jj * DP + a] = p.X[(size_t)i * DP + a];
+            if (a == 0) {
+                s.ib[jj] = i;
+                const int uid = __ldcg(p.z_uid + i);
+                s.uidb[jj] = uid;
+                s.ub[jj] = p.u[j];
+                s.lpb[jj] = p.log_prior[i];
+                kob[jj] = uid >= 0 ? s.slot_of_uid[uid] : -1;
+            }
+        }
+        bar_sync_all();
+        F_PROF(PH_STAGE);
+        int K = sh.K;
+        int done = 0;
+        for (int jj = 0; jj < nb; ++jj) {
+            seq += 1;
+            const int k_old = kob[jj];
+            bool rare = (k_old < 0) || (K >= SEQ_KMAX);
+            int k_new = -1;
+            if (!rare) {
+                const double *x = xb + jj * DP;
+                // ---- phase A: the quadratic forms, four threads per component ----
+                double pq = 0.0;
+                if (k < K) pq = seq_quad_part<DP, PART, ST>(B, mu, x);
+                if constexpr (PART > 0) psum[(PART - 1) * SEQ_KMAX + k] = pq;
+                bar_sync_all();                                                        // #1
+                if constexpr (PART == 0) {
+                    // ---- finish the K + 1 weights, scan them, draw (crpmm.py:68-78, utils.py:7-20) ----
+                    const double wref = p.log_alpha + lpb[jj];   // the new-table weight (crpmm.py:74) is the exp scale
+                    double e = 0.0;
+                    if (k < K) {
+                        const double q = 2.0 * ((pq + psum[k]) + (psum[SEQ_KMAX + k] + psum[2 * SEQ_KMAX + k]));
+                        const int own = (k == k_old) ? 1 : 0;
+                        e = f_finish_weight<ST>(sc, q, own, wref, fmtab);
+                        qv[k] = q;
+                        // untrusted closed form, or the datum is its component's last member: the general step
+                        if (e != e || (own && sc[F_N * ST] == 1.0)) sh.rare_seq = seq;
+                    } else if (k == K) {
+                        e = 1.0;
+                    }
+                    double incl = e;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    if (lane == 31) sh.wtot[warp] = incl;
+                    bar_sync_front();                                                  // #2 (warps 0..3)
+                    const double w0 = sh.wtot[0], w1 = sh.wtot[1], w2 = sh.wtot[2], w3 = sh.wtot[3];
+                    const double p1 = w0, p2 = w0 + w1, p3 = p2 + w2, tot = p3 + w3;
+                    const double t0 = ub[jj] * tot;
+                    const int hitw = (p1 > t0) ? 0 : (p2 > t0) ? 1 : (p3 > t0) ? 2 : (tot > t0) ? 3 : 4;
+                    if (warp == hitw) {
+                        const double pre = (warp == 0) ? 0.0 : (warp == 1) ? p1 : (warp == 2) ? p2 : p3;
+                        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                        if (lane == 0) excl = 0.0;
+                        const double upper = pre + incl, lower = pre + excl;
+                        const unsigned who = __ballot_sync(0xffffffffu, upper > t0);
+                        if (who != 0u && lane == __ffs(who) - 1) {
+                            sh.k_new = tid;
+                            sh.last_mg = (double)__fdividef((float)fmin(t0 - lower, upper - t0), (float)tot);
+                        }
+                    }
+                    if (tid == 0) {
+                        if (hitw == 4) { sh.k_new = K; sh.last_mg = 0.0; }   // utils.py:20 fallback: the last index
+                        if (!(tot > 0.0) || !(tot < INFINITY)) sh.rare_seq = seq;
+                    }
+                }
+                bar_sync_all();                                                        // #3
+                F_PROF(PH_EVAL);
+                k_new = sh.k_new;
+                const double mg = sh.last_mg;
+                // a birth, a draw inside the margin guard, or anything flagged above: the general step redoes the datum
+                rare = (sh.rare_seq == seq) || (k_new >= K) || (mg < p.guard);
+                if (!rare && tid == 0) {
+                    sh.evals += K;
+                    sh.fast_steps += 1;
+                    const unsigned long long mb = (unsigned long long)__double_as_longlong(mg);
+                    if (mb < sh.margin_bits) sh.margin_bits = mb;
+                }
+            }
+            if (rare) {
+                // registers back to the shared-memory records, the general step (bgmm_fast.cuh), registers again
+                seq_store_block<DP, PART, ST>(col, B);
+                bar_sync_all();
+                f_step<DP>(p, s, jj, seq);
+                bar_sync_all();
+                F_PROF(PH_RARE);
+                if (sh.error) break;
+                seq_load_block<DP, PART, ST>(col, B);
+                K = sh.K;
+                // deaths renumber slots: the staged data's own components again
+                if (tid > jj && tid < nb) { const int uid = s.uidb[tid]; kob[tid] = uid >= 0 ? s.slot_of_uid[uid] : -1; }
+                bar_sync_all();
+                done = jj + 1;
+                continue;
+            }
+            F_COUNT(PH_STEPS);
+            done = jj + 1;
+            if (k_new == k_old) continue;   // stay: nothing was touched (crpmm.py:82-85)
+
+            // ---- the datum moves from k_old to k_new, both live (add_item / del_item, gaussian_components.py:154-186) ----
+            // Nothing but the B block lives across barrier #4: what the second half needs is re-read from shared memory.
+            const bool mine = (k == k_old) || (k == k_new);
+            const int which = (k == k_new) ? 1 : 0;
+            double *vp = vpb + which * 3 * DP;
+            if (mine) {
+                const double *x = xb + jj * DP;
+                if constexpr (PART == 0) {
+                    // count-table rows n2 - 1 and n2 straight into shared memory (cp.async: an L2 round trip that costs
+                    // no register and is first waited for after the matrix update)
+                    const long long n_cur = (long long)sc[F_N * ST];
+                    const double *r0 = p.ntab + (size_t)(n_cur + (which ? 0 : -2)) * NT_W;
+                    const uint32_t dst = smem_u32(ntb + which * 8);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(r0) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(r0 + NT_W) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 32), "l"(r0 + NT_W + 2) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 48), "l"(r0 + NT_W + 4) : "memory");
+                    // beta = kappa / (kappa -+ 1): BETA(n) for the removal, G(n) for the addition
+                    const double beta = which ? sc[F_G * ST] : sc[F_BETA * ST];
+                    const double sq = qv[k];
+                    const double den = which ? 1.0 + beta * sq : 1.0 - beta * sq;
+                    // 1 / den without a division (its slow path is a call, and a call with the B block live would put
+                    // part of the block on the stack): single-precision seed, three Newton steps
+                    float rf;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)den));
+                    double rd = (double)rf;
+                    rd = fma(rd, fma(-den, rd, 1.0), rd);
+                    rd = fma(rd, fma(-den, rd, 1.0), rd);
+                    rd = fma(rd, fma(-den, rd, 1.0), rd);
+                    gdb[which * 2] = which ? -(beta * rd) : beta * rd;
+                    gdb[which * 2 + 1] = den;
+                }
+                seq_partial_v<DP, PART, ST>(B, mu, x, vp);
+            }
+            if (p.writer && warp >= 8) {
+                // the bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition)
+                const double *xg = s.xb + jj * DP;
+                if (warp < 12) {
+                    f_stats_axpy_inl<DP>(p, s.rc, k_old, xg, -1, 0, tid - 256, 128);
+                } else {
+                    f_stats_axpy_inl<DP>(p, s.rc, k_new, xg, +1, 0, tid - 384, 128);
+                    if (tid == 384) __stcg(p.z_out + ib[jj], s.uid_of_slot[k_new]);
+                }
+            }
+            bar_sync_all();                                                            // #4
+            if (mine) {
+                seq_rank_one<DP, PART>(B, vp, gdb[which * 2]);
+                if constexpr (PART == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+            }
+            bar_sync_all();                                                            // #4b: the count-table rows landed
+            if (mine) {
+                const double *nt = ntb + which * 8;   // r0: CN, G | r1: CN, G, H, BETA, RK
+                if constexpr (G::TRI) {
+                    // m' = m -+ d / kappa(n2), d = m - x  (this thread is the only writer of these means)
+                    const double *x = xb + jj * DP;
+                    const double rk2 = which ? -nt[6] : nt[6];
+#pragma unroll
+                    for (int a = 0; a < G::TN; ++a) {
+                        double *pm = col + (Ly::MU + G::O + a) * ST;
+                        const double m = *pm;
+                        *pm = fma(m - x[G::O + a], rk2, m);
+                    }
+                }
+                if constexpr (PART == 0) {
+                    const double n2 = sc[F_N * ST] + (which ? 1.0 : -1.0);
+                    const double lds = sc[F_LDS * ST] + fm::f_log(gdb[which * 2 + 1], fmtab);   // matrix determinant lemma
+                    const double cnt = sc[F_CNT * ST] + 1.0;
+                    sc[F_N * ST] = n2;
+                    sc[F_LDS * ST] = lds;
+                    sc[F_CNT * ST] = cnt;
+                    sc[F_CW * ST] = nt[2] - 0.5 * lds;
+                    sc[F_G * ST] = nt[3];
+                    sc[F_H * ST] = nt[4];
+                    sc[F_BETA * ST] = nt[5];
+                    sc[F_CWO * ST] = nt[0] - 0.5 * lds;
+                    if (cnt >= (double)REFRESH_EVERY) { if (which == 0) sh.refresh_a = seq; else sh.refresh_b = seq; }
+                    if (which == 1) sh.moves += 1;
+                }
+            }
+            bar_sync_all();                                                            // #5
+            F_PROF(PH_UPDATE);
+            F_COUNT(PH_MOVES);
+            const bool ra = (sh.refresh_a == seq), rb = (sh.refresh_b == seq);
+            if (ra || rb) {
+                // drift control: the record(s) again from the bit-exact statistics (needs the shared-memory records)
+                seq_store_block<DP, PART, ST>(col, B);
+                bar_sync_all();
+                const double n_a = ra ? rec[(Ly::SC + F_N) * ST + k_old] : 0.0;
+                const double n_b = rec[(Ly::SC + F_N) * ST + k_new];
+                f_refresh<DP>(p, s, ra ? k_old : -1, n_a, rb ? k_new : -1, n_b);
+                seq_load_block<DP, PART, ST>(col, B);
+                // the rebuild used the scratch that holds the staged data's own components: look them up again
+                if (tid > jj && tid < nb) { const int uid = s.uidb[tid]; kob[tid] = uid >= 0 ? s.slot_of_uid[uid] : -1; }
+                bar_sync_all();
+                F_PROF(PH_RARE);
+            }
+        }
+        bar_sync_all();
+        if (tid == 0) {
+            const long long mv = sh.moves - sh.seq_moves0;
+            sh.gap = 0.5 * sh.gap + 0.5 * (double)nb / ((double)mv + 0.5);
+            sh.seq_data += done;
+            sh.pos = sh.pos + done;
+            if (p.engine == 0 && sh.gap >= (double)p.gap_to_win) sh.mode = 1;
+            sh.win = f_next_window(sh.gap, sh.pos, p.N, p.win_factor);
+        }
+        bar_sync_all();
+    }
+    // registers back to the shared-memory records; the window evaluators' cached rows are void
+    seq_store_block<DP, PART, ST>(col, B);
+    if (tid == 0) { sh.ver += 1; sh.dall_ver = sh.ver; }
+    bar_sync_all();
+    return seq;
+}
+
+// dispatch by warp: part = warp / 4
+template <int DP> __device__ __forceinline__ int f_seq_run(const Params &p, const FSmem<DP> &s, int seq) {
+    switch (threadIdx.x >> 7) {
+        case 0: return f_seq_part<DP, 0>(p, s, seq);
+        case 1: return f_seq_part<DP, 1>(p, s, seq);
+        case 2: return f_seq_part<DP, 2>(p, s, seq);
+        default: return f_seq_part<DP, 3>(p, s, seq);
+    }
+}
+
+}  // namespace fast
+}  // namespace bgmm
