@@ -1650,6 +1650,108 @@ __device__ __forceinline__ long long f_next_window(double gap, long long pos, lo
     return left < (long long)win ? left : (long long)win;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Window mode: speculative rounds (f_window_eval / f_bulk_eval -> one grid barrier -> every CTA applies the first
+// candidate) until the running gap between movers says sequential steps pay, the sweep ends, or an error.  Out of line
+// and self-contained (its own evaluator cache: after sequential batches the cached rows are void anyway) so that its
+// working set does not share a register allocation with the call sites of the sequential engine -- what does not fit
+// in registers goes to local memory, and local memory has next to no L1 under ~220 KB of shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int DP>
+__device__ __noinline__ int f_window_run(const Params &p, const FSmem<DP> &s, int seq) {
+    FSh &sh = *s.sh;
+    Ctl *ctl = p.ctl;
+    const int tid = threadIdx.x;
+    const bool cta0 = (p.writer != 0);
+    WCache cache;
+    cache.nj = (long long)blockIdx.x + (long long)gridDim.x * (tid >> 5);
+    cache.j = -1; cache.i = 0; cache.uid = -1; cache.stage = 0; cache.ver = -1; cache.K = 0; cache.u = 0.0; cache.lp = 0.0;
+    // minimum margin over this warp's window evaluations (committed and discarded alike: a lower bound of the
+    // chain's true minimum margin); folded into the control block on the way out
+    double win_margin = 1.0;
+    while (true) {
+        const long long pos = sh.pos;
+        if (pos >= p.N || sh.error != 0 || sh.mode != 1) break;
+        {
+            const unsigned int r = sh.round;
+            unsigned long long *slot = &ctl->first3[r % 3u][0];
+            if (cta0 && tid == 0) __stcg(&ctl->first3[(r + 1u) % 3u][0], ~0ULL >> 1);
+            const int K = sh.K;
+            const long long win = sh.win;
+            F_PROF(PH_HEAD);
+            const bool bulk = (win >= (long long)gridDim.x * BULK_MIN_ROWS);
+            if (bulk) f_bulk_eval<DP>(p, s, pos, win, K, slot, win_margin);
+            else f_window_eval<DP>(p, s, pos, win, K, slot, r, cache, win_margin);
+#ifdef BGMM_PROFILE
+            __syncthreads();   // only to attribute the waiting to the right phase clock
+#endif
+            F_PROF(PH_WINEVAL);
+            f_round_barrier(ctl, slot, r + 1u, &sh.fv);
+            F_PROF(PH_BARRIER);
+            F_COUNT(PH_ROUNDS);
+            const unsigned long long fv = sh.fv;
+            const long long f = (long long)(fv >> 12);
+            const long long end = pos + win;
+            if (f < end && (fv & 4095ULL) == BULK_TAG) {
+                // candidate of the thread-per-datum evaluator: stage it from global memory and resolve it in full
+                if (tid == 0) { sh.evals += (f - pos) * (long long)K; sh.wasted += end - (f + 1); }
+                __syncthreads();
+                f_run<DP>(p, s, f, 1, seq);
+                __syncthreads();
+                if (tid == 0) {
+                    sh.pos = f + (sh.error ? 0 : 1);
+                    sh.gap = 0.7 * sh.gap + 0.3 * (double)(f - pos + 1);
+                }
+            } else if (f < end) {
+                // every CTA resolves the first candidate itself, from the inputs its evaluator published
+                const double *mv = p.mvbuf + ((size_t)(r & 1u) * gridDim.x * NWARP + (size_t)(fv & 4095ULL)) * (DP + MV_EXTRA);
+                if (tid < DP + MV_EXTRA) {
+                    const double v = __ldcg(mv + tid);
+                    if (tid < DP) s.xb[tid] = v;
+                    else if (tid == DP) s.ub[0] = v;
+                    else if (tid == DP + 1) s.lpb[0] = v;
+                    else if (tid == DP + 2) s.ib[0] = __double_as_longlong(v);
+                    else if (tid == DP + 3) s.uidb[0] = (int)__double_as_longlong(v);
+                    else sh.k_new = (int)__double_as_longlong(v);
+                }
+                if (tid == 0) { sh.evals += (f - pos) * (long long)K; sh.wasted += end - (f + 1); }
+                __syncthreads();
+                const int drawn = sh.k_new;
+                F_PROF(PH_STAGE);
+                seq += 1;
+                if (drawn >= 0) {
+                    // a plain move, already drawn by its evaluator against the current records
+                    if (tid == 0) sh.evals += K;
+                    f_move_phase<DP>(p, s, 0, s.slot_of_uid[s.uidb[0]], drawn, true, false, false, false, seq);
+                } else {
+                    f_step<DP>(p, s, 0, seq);
+                    __syncthreads();   // f_step can return without a trailing barrier (stay / error paths)
+                }
+                if (tid == 0) {
+                    sh.pos = f + (sh.error ? 0 : 1);
+                    sh.gap = 0.7 * sh.gap + 0.3 * (double)(f - pos + 1);
+                }
+            } else if (tid == 0) {
+                sh.evals += win * (long long)K;
+                sh.pos = end;
+                sh.gap = fmax(sh.gap, 0.7 * sh.gap + 0.3 * 2.0 * (double)win);
+            }
+            if (tid == 0) {
+                sh.windows += 1;
+                sh.round = r + 1u;
+                if (p.engine == 0 && sh.gap < (double)p.gap_to_seq) sh.mode = 0;
+                sh.win = f_next_window(sh.gap, sh.pos, p.N, p.win_factor);
+            }
+                }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) win_margin = fmin(win_margin, __shfl_xor_sync(0xffffffffu, win_margin, o));
+    if ((tid & 31) == 0 && win_margin < 1.0)
+        atomicMin(&ctl->margin_bits, (unsigned long long)__double_as_longlong(win_margin));
+    return seq;
+}
+
 }  // namespace fast
 }  // namespace bgmm
 #include "bgmm_seq.cuh"
@@ -1768,13 +1870,7 @@ __device__ __forceinline__ void fast_sweep_body(const Params &p_in) {
     // no replica may still be reading the initial state when CTA 0 starts changing it
     f_grid_barrier(p);
 
-    WCache cache;
-    cache.nj = (long long)blockIdx.x + (long long)gridDim.x * (tid >> 5);
-    cache.j = -1; cache.i = 0; cache.uid = -1; cache.stage = 0; cache.ver = -1; cache.K = 0; cache.u = 0.0; cache.lp = 0.0;
     int seq = 0;
-    // minimum margin over this warp's window evaluations (committed and discarded alike: a lower bound of the
-    // chain's true minimum margin); folded into the control block once, at the end
-    double win_margin = 1.0;
 
     // ---- main loop ----
     while (true) {
@@ -1786,7 +1882,6 @@ __device__ __forceinline__ void fast_sweep_body(const Params &p_in) {
             // change mode, K outgrows its layout, or the sweep ends
             __syncthreads();
             seq = f_seq_run<DP>(p, s, seq);
-            cache.j = -1; cache.stage = 0;   // its staging reuses nothing of the evaluators', but their rows are void
         } else if (mode == 0) {
             const int nb = (int)min((long long)SEQ_BATCH, p.N - pos);
             const long long moves0 = sh.moves;
@@ -1803,85 +1898,15 @@ __device__ __forceinline__ void fast_sweep_body(const Params &p_in) {
                 sh.win = f_next_window(sh.gap, sh.pos, p.N, p.win_factor);
             }
         } else {
-            const unsigned int r = sh.round;
-            unsigned long long *slot = &ctl->first3[r % 3u][0];
-            if (cta0 && tid == 0) __stcg(&ctl->first3[(r + 1u) % 3u][0], ~0ULL >> 1);
-            const int K = sh.K;
-            const long long win = sh.win;
-            F_PROF(PH_HEAD);
-            const bool bulk = (win >= (long long)gridDim.x * BULK_MIN_ROWS);
-            if (bulk) f_bulk_eval<DP>(p, s, pos, win, K, slot, win_margin);
-            else f_window_eval<DP>(p, s, pos, win, K, slot, r, cache, win_margin);
-#ifdef BGMM_PROFILE
-            __syncthreads();   // only to attribute the waiting to the right phase clock
-#endif
-            F_PROF(PH_WINEVAL);
-            f_round_barrier(ctl, slot, r + 1u, &sh.fv);
-            F_PROF(PH_BARRIER);
-            F_COUNT(PH_ROUNDS);
-            const unsigned long long fv = sh.fv;
-            const long long f = (long long)(fv >> 12);
-            const long long end = pos + win;
-            if (f < end && (fv & 4095ULL) == BULK_TAG) {
-                // candidate of the thread-per-datum evaluator: stage it from global memory and resolve it in full
-                if (tid == 0) { sh.evals += (f - pos) * (long long)K; sh.wasted += end - (f + 1); }
-                __syncthreads();
-                f_run<DP>(p, s, f, 1, seq);
-                __syncthreads();
-                if (tid == 0) {
-                    sh.pos = f + (sh.error ? 0 : 1);
-                    sh.gap = 0.7 * sh.gap + 0.3 * (double)(f - pos + 1);
-                }
-            } else if (f < end) {
-                // every CTA resolves the first candidate itself, from the inputs its evaluator published
-                const double *mv = p.mvbuf + ((size_t)(r & 1u) * gridDim.x * NWARP + (size_t)(fv & 4095ULL)) * (DP + MV_EXTRA);
-                if (tid < DP + MV_EXTRA) {
-                    const double v = __ldcg(mv + tid);
-                    if (tid < DP) s.xb[tid] = v;
-                    else if (tid == DP) s.ub[0] = v;
-                    else if (tid == DP + 1) s.lpb[0] = v;
-                    else if (tid == DP + 2) s.ib[0] = __double_as_longlong(v);
-                    else if (tid == DP + 3) s.uidb[0] = (int)__double_as_longlong(v);
-                    else sh.k_new = (int)__double_as_longlong(v);
-                }
-                if (tid == 0) { sh.evals += (f - pos) * (long long)K; sh.wasted += end - (f + 1); }
-                __syncthreads();
-                const int drawn = sh.k_new;
-                F_PROF(PH_STAGE);
-                seq += 1;
-                if (drawn >= 0) {
-                    // a plain move, already drawn by its evaluator against the current records
-                    if (tid == 0) sh.evals += K;
-                    f_move_phase<DP>(p, s, 0, s.slot_of_uid[s.uidb[0]], drawn, true, false, false, false, seq);
-                } else {
-                    f_step<DP>(p, s, 0, seq);
-                    __syncthreads();   // f_step can return without a trailing barrier (stay / error paths)
-                }
-                if (tid == 0) {
-                    sh.pos = f + (sh.error ? 0 : 1);
-                    sh.gap = 0.7 * sh.gap + 0.3 * (double)(f - pos + 1);
-                }
-            } else if (tid == 0) {
-                sh.evals += win * (long long)K;
-                sh.pos = end;
-                sh.gap = fmax(sh.gap, 0.7 * sh.gap + 0.3 * 2.0 * (double)win);
-            }
-            if (tid == 0) {
-                sh.windows += 1;
-                sh.round = r + 1u;
-                if (p.engine == 0 && sh.gap < (double)p.gap_to_seq) sh.mode = 0;
-                sh.win = f_next_window(sh.gap, sh.pos, p.N, p.win_factor);
-            }
+            // sparse movers: speculative window rounds until the engine should change mode or the sweep ends
+            __syncthreads();
+            seq = f_window_run<DP>(p, s, seq);
         }
         __syncthreads();
     }
 
     // ---- epilogue: CTA 0 publishes the chain state ----
     __syncthreads();
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) win_margin = fmin(win_margin, __shfl_xor_sync(0xffffffffu, win_margin, o));
-    if ((tid & 31) == 0 && win_margin < 1.0)
-        atomicMin(&ctl->margin_bits, (unsigned long long)__double_as_longlong(win_margin));
     if (cta0) {
         const int K = sh.K;
         for (int t = tid; t < p.K_max; t += TF) {

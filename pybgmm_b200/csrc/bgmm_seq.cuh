@@ -9,9 +9,10 @@
 // Why it exists: when most data move, the chain is one serial step per datum and the step's latency is the whole
 // story.  f_step streams every live record through shared memory for every datum (K x 1.2 KB at D = 16: the 128 B/clk
 // shared-memory port alone is ~1.4 k cycles per datum) and chains five CTA barriers through out-of-line phases.  Here
-//   * the matrices B_k = S_N^-1 of all live components live in REGISTERS for the whole run: thread (k, part) of the
-//     CTA owns one of four blocks of B_k -- the two diagonal triangles LL / HH and the two row-halves of the
-//     off-diagonal block (D = 16: 36 / 36 / 32 / 32 doubles, 72 of the thread's 128 registers); `part` is warp-uniform
+//   * the matrices B_k = S_N^-1 of all live components live (mostly) in REGISTERS for the whole run: thread (k, part)
+//     of the CTA owns one of four blocks of B_k -- the two diagonal triangles LL / HH and the two row-halves of the
+//     off-diagonal block (D = 16: 36 / 36 / 32 / 32 doubles, of which 24 sit in registers and the rest is read
+//     from the shared-memory record: more would spill, and spills go to L2 here); `part` is warp-uniform
 //     (warps 4 part .. 4 part + 3), lanes run over components: no divergence, and an evaluation reads only the mean
 //     and x from shared memory (8-12 doubles per thread instead of 44);
 //   * a datum that stays costs three barriers (partial sums, scan of the 4 x 32 choices, draw); a move adds two:
@@ -41,7 +42,17 @@ template <int DP, int PART> struct Blk {
     static constexpr int R0 = PART == 2 ? H : H + R2;      // RECT: first row
     static constexpr int RN = PART == 2 ? R2 : NU - R2;    // RECT: rows (columns are L)
     static constexpr int NE = TRI ? TN * (TN + 1) / 2 : RN * H;
-    static constexpr int NEA = NE > 0 ? NE : 1;
+    // of the block's NE elements the first NR (in the block's own packed order) live in registers, the rest stay in
+    // the shared-memory record: 24 doubles + the step's working set fit the 128-register budget of a 512-thread CTA
+    // without spilling (local memory has almost no L1 here -- shared memory takes ~220 KB of the SM's 256 KB)
+    static constexpr int RCAP = 24;
+    static constexpr int NR = NE > RCAP ? RCAP : NE;
+    static constexpr int NEA = NR > 0 ? NR : 1;
+    // local packed index / global packed index (row-major lower triangle of the DP x DP matrix) of element (a, b)
+    __host__ __device__ static constexpr int le(int a, int b) { return TRI ? a * (a + 1) / 2 + b : a * H + b; }
+    __host__ __device__ static constexpr int ge(int a, int b) {
+        return TRI ? (O + a) * (O + a + 1) / 2 + O + b : (R0 + a) * (R0 + a + 1) / 2 + b;
+    }
     static constexpr int TNA = TN > 0 ? TN : 1;
     static constexpr int RNA = RN > 0 ? RN : 1;
 };
@@ -49,7 +60,23 @@ template <int DP, int PART> struct Blk {
 __device__ __forceinline__ void bar_sync_all() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_front() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // warps 0..3
 
-// registers <-> shared-memory records (element-major rec[e * ST + k])
+// element (a, b) of this thread's block: a register, or the shared-memory record (col = element 0 of the component,
+// element-major rec[e * ST + k]).  a, b are compile-time after unrolling, so the choice costs nothing.
+template <int DP, int PART, int ST>
+__device__ __forceinline__ double bget(const double (&B)[Blk<DP, PART>::NEA], const double *__restrict__ col, int a, int b) {
+    using G = Blk<DP, PART>;
+    const int l = G::le(a, b);
+    return l < G::NR ? B[l < G::NR ? l : 0] : col[G::ge(a, b) * ST];
+}
+template <int DP, int PART, int ST>
+__device__ __forceinline__ void bset(double (&B)[Blk<DP, PART>::NEA], double *__restrict__ col, int a, int b, double v) {
+    using G = Blk<DP, PART>;
+    const int l = G::le(a, b);
+    if (l < G::NR) B[l < G::NR ? l : 0] = v;
+    else col[G::ge(a, b) * ST] = v;
+}
+
+// registers <-> shared-memory records: only the register-resident elements move
 template <int DP, int PART, int ST>
 __device__ __forceinline__ void seq_load_block(const double *__restrict__ col, double (&B)[Blk<DP, PART>::NEA]) {
     using G = Blk<DP, PART>;
@@ -57,12 +84,14 @@ __device__ __forceinline__ void seq_load_block(const double *__restrict__ col, d
 #pragma unroll
         for (int a = 0; a < G::TN; ++a)
 #pragma unroll
-            for (int b = 0; b <= a; ++b) B[a * (a + 1) / 2 + b] = col[((G::O + a) * (G::O + a + 1) / 2 + G::O + b) * ST];
+            for (int b = 0; b <= a; ++b)
+                if (G::le(a, b) < G::NR) B[G::le(a, b) < G::NR ? G::le(a, b) : 0] = col[G::ge(a, b) * ST];
     } else {
 #pragma unroll
         for (int a = 0; a < G::RN; ++a)
 #pragma unroll
-            for (int b = 0; b < G::H; ++b) B[a * G::H + b] = col[((G::R0 + a) * (G::R0 + a + 1) / 2 + b) * ST];
+            for (int b = 0; b < G::H; ++b)
+                if (G::le(a, b) < G::NR) B[G::le(a, b) < G::NR ? G::le(a, b) : 0] = col[G::ge(a, b) * ST];
     }
 }
 template <int DP, int PART, int ST>
@@ -72,20 +101,22 @@ __device__ __forceinline__ void seq_store_block(double *__restrict__ col, const 
 #pragma unroll
         for (int a = 0; a < G::TN; ++a)
 #pragma unroll
-            for (int b = 0; b <= a; ++b) col[((G::O + a) * (G::O + a + 1) / 2 + G::O + b) * ST] = B[a * (a + 1) / 2 + b];
+            for (int b = 0; b <= a; ++b)
+                if (G::le(a, b) < G::NR) col[G::ge(a, b) * ST] = B[G::le(a, b) < G::NR ? G::le(a, b) : 0];
     } else {
 #pragma unroll
         for (int a = 0; a < G::RN; ++a)
 #pragma unroll
-            for (int b = 0; b < G::H; ++b) col[((G::R0 + a) * (G::R0 + a + 1) / 2 + b) * ST] = B[a * G::H + b];
+            for (int b = 0; b < G::H; ++b)
+                if (G::le(a, b) < G::NR) col[G::ge(a, b) * ST] = B[G::le(a, b) < G::NR ? G::le(a, b) : 0];
     }
 }
 
 // this block's share of  sum_a d_a (sum_{b<a} B_ab d_b + B_aa d_a / 2),  d = m - x;  q = 2 * (sum over the four parts).
 // Same operation order as f_quad_part16.
 template <int DP, int PART, int ST>
-__device__ __forceinline__ double seq_quad_part(const double (&B)[Blk<DP, PART>::NEA], const double *__restrict__ mu,
-                                                const double *__restrict__ x) {
+__device__ __forceinline__ double seq_quad_part(const double (&B)[Blk<DP, PART>::NEA], const double *__restrict__ col,
+                                                const double *__restrict__ mu, const double *__restrict__ x) {
     using G = Blk<DP, PART>;
     double q = 0.0;
     if constexpr (G::TRI) {
@@ -96,8 +127,8 @@ __device__ __forceinline__ double seq_quad_part(const double (&B)[Blk<DP, PART>:
         for (int a = 0; a < G::TN; ++a) {
             double r = 0.0;
 #pragma unroll
-            for (int b = 0; b < a; ++b) r = fma(B[a * (a + 1) / 2 + b], d[b], r);
-            r = fma(0.5 * B[a * (a + 1) / 2 + a], d[a], r);
+            for (int b = 0; b < a; ++b) r = fma(bget<DP, PART, ST>(B, col, a, b), d[b], r);
+            r = fma(0.5 * bget<DP, PART, ST>(B, col, a, a), d[a], r);
             q = fma(d[a], r, q);
         }
     } else {
@@ -110,7 +141,7 @@ __device__ __forceinline__ double seq_quad_part(const double (&B)[Blk<DP, PART>:
         for (int a = 0; a < G::RN; ++a) {
             double r = 0.0;
 #pragma unroll
-            for (int b = 0; b < G::H; ++b) r = fma(B[a * G::H + b], dl[b], r);
+            for (int b = 0; b < G::H; ++b) r = fma(bget<DP, PART, ST>(B, col, a, b), dl[b], r);
             q = fma(dh[a], r, q);
         }
     }
@@ -121,21 +152,20 @@ __device__ __forceinline__ double seq_quad_part(const double (&B)[Blk<DP, PART>:
 //   slot 0: LL -> [0, H), UU -> [H, DP);  slot 1: part 2 -> [0, H) and its rows, part 3 -> its rows;
 //   slot 2: part 3 -> [0, H).  v_a = (slot0 + slot1) + slot2 (slot 2 only for a < H).  Empty blocks write zeros.
 template <int DP, int PART, int ST>
-__device__ __forceinline__ void seq_partial_v(const double (&B)[Blk<DP, PART>::NEA], const double *__restrict__ mu,
-                                              const double *__restrict__ x, double *__restrict__ vp) {
+__device__ __forceinline__ void seq_partial_v(const double (&B)[Blk<DP, PART>::NEA], const double *__restrict__ col,
+                                              const double *__restrict__ mu, const double *__restrict__ x,
+                                              double *__restrict__ vp) {
     using G = Blk<DP, PART>;
     if constexpr (G::TRI) {
-        double dkeep[G::TNA];
+        double d[G::TNA];
 #pragma unroll
-        for (int a = 0; a < G::TN; ++a) dkeep[a] = mu[(G::O + a) * ST] - x[G::O + a];
+        for (int a = 0; a < G::TN; ++a) d[a] = mu[(G::O + a) * ST] - x[G::O + a];
 #pragma unroll
         for (int a = 0; a < G::TN; ++a) {
             double acc = 0.0;
 #pragma unroll
-            for (int b = 0; b < G::TN; ++b) {
-                const int e = (a >= b) ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a;
-                acc = fma(B[e], dkeep[b], acc);
-            }
+            for (int b = 0; b < G::TN; ++b)
+                acc = fma(a >= b ? bget<DP, PART, ST>(B, col, a, b) : bget<DP, PART, ST>(B, col, b, a), d[b], acc);
             vp[G::O + a] = acc;
         }
     } else {
@@ -148,22 +178,23 @@ __device__ __forceinline__ void seq_partial_v(const double (&B)[Blk<DP, PART>::N
         for (int a = 0; a < G::RN; ++a) {
             double acc = 0.0;
 #pragma unroll
-            for (int b = 0; b < G::H; ++b) acc = fma(B[a * G::H + b], dl[b], acc);
+            for (int b = 0; b < G::H; ++b) acc = fma(bget<DP, PART, ST>(B, col, a, b), dl[b], acc);
             vp[DP + G::R0 + a] = acc;
         }
 #pragma unroll
         for (int b = 0; b < G::H; ++b) {
             double acc = 0.0;
 #pragma unroll
-            for (int a = 0; a < G::RN; ++a) acc = fma(B[a * G::H + b], dh[a], acc);
+            for (int a = 0; a < G::RN; ++a) acc = fma(bget<DP, PART, ST>(B, col, a, b), dh[a], acc);
             vp[(PART == 2 ? DP : 2 * DP) + b] = acc;
         }
     }
 }
 
 // B += gam v v^T on this block, v combined from the partial-product slots
-template <int DP, int PART>
-__device__ __forceinline__ void seq_rank_one(double (&B)[Blk<DP, PART>::NEA], const double *__restrict__ vp, double gam) {
+template <int DP, int PART, int ST>
+__device__ __forceinline__ void seq_rank_one(double (&B)[Blk<DP, PART>::NEA], double *__restrict__ col,
+                                             const double *__restrict__ vp, double gam) {
     using G = Blk<DP, PART>;
     auto vat = [&](int a) -> double {
         const double t = vp[a] + vp[DP + a];
@@ -177,7 +208,7 @@ __device__ __forceinline__ void seq_rank_one(double (&B)[Blk<DP, PART>::NEA], co
         for (int a = 0; a < G::TN; ++a) {
             const double ga = gam * v[a];
 #pragma unroll
-            for (int b = 0; b <= a; ++b) B[a * (a + 1) / 2 + b] = fma(ga, v[b], B[a * (a + 1) / 2 + b]);
+            for (int b = 0; b <= a; ++b) bset<DP, PART, ST>(B, col, a, b, fma(ga, v[b], bget<DP, PART, ST>(B, col, a, b)));
         }
     } else {
         double vl[G::H], vh[G::RNA];
@@ -189,7 +220,7 @@ __device__ __forceinline__ void seq_rank_one(double (&B)[Blk<DP, PART>::NEA], co
         for (int a = 0; a < G::RN; ++a) {
             const double ga = gam * vh[a];
 #pragma unroll
-            for (int b = 0; b < G::H; ++b) B[a * G::H + b] = fma(ga, vl[b], B[a * G::H + b]);
+            for (int b = 0; b < G::H; ++b) bset<DP, PART, ST>(B, col, a, b, fma(ga, vl[b], bget<DP, PART, ST>(B, col, a, b)));
         }
     }
 }
@@ -213,12 +244,14 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     const double *xb = smem_raw + O::XB;
     const double *ub = smem_raw + O::UB, *lpb = smem_raw + O::LPB;
     const long long *ib = reinterpret_cast<const long long *>(smem_raw + O::IB);
-    double *psum = smem_raw + O::A;                          // A and W are contiguous: 3 x 128 partial sums
+    // the window evaluators' rows (ew rows 0..NWARP-1) are idle, and void, while the chain runs sequentially:
+    double *psum = smem_raw + O::EW;                         // 3 x 128 partial sums of the quadratic forms,
+    int *kob = reinterpret_cast<int *>(psum + 3 * SEQ_KMAX); // slots of the staged data's own components (SEQ_BATCH ints),
+    double *rkb = psum + 3 * SEQ_KMAX + SEQ_BATCH / 2;       // 2 x 2: the UU owner's count-table chunk (cp.async target)
     double *qv = smem_raw + O::EW + NWARP * Ly::WS;          // f_step's row: the quadratic forms of this datum
     double *vpb = smem_raw + O::DV;                          // dv, vv, nt are contiguous: 2 x 3 x DP partial products
     double *ntb = qv + SEQ_KMAX;                             // 2 x 8 count-table entries (cp.async targets, 16-B aligned)
     double *gdb = ntb + 16;                                  // (gam, den) of the two rank-one updates
-    int *kob = reinterpret_cast<int *>(smem_raw + O::MM);    // slot of the staged data's own components
     const double *fmtab = smem_raw + O::FM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = tid & (SEQ_KMAX - 1);
@@ -264,7 +297,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                 const double *x = xb + jj * DP;
                 // ---- phase A: the quadratic forms, four threads per component ----
                 double pq = 0.0;
-                if (k < K) pq = seq_quad_part<DP, PART, ST>(B, mu, x);
+                if (k < K) pq = seq_quad_part<DP, PART, ST>(B, col, mu, x);
                 if constexpr (PART > 0) psum[(PART - 1) * SEQ_KMAX + k] = pq;
                 bar_sync_all();                                                        // #1
                 if constexpr (PART == 0) {
@@ -374,7 +407,14 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                     gdb[which * 2] = which ? -(beta * rd) : beta * rd;
                     gdb[which * 2 + 1] = den;
                 }
-                seq_partial_v<DP, PART, ST>(B, mu, x, vp);
+                if constexpr (PART == 1) {
+                    // 1 / kappa(n2) for the means this thread owns: its own copy of that count-table chunk
+                    const long long n_cur = (long long)sc[F_N * ST];
+                    const double *r1 = p.ntab + (size_t)(n_cur + (which ? 1 : -1)) * NT_W;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(rkb + which * 2)), "l"(r1 + NT_RK)
+                                 : "memory");
+                }
+                seq_partial_v<DP, PART, ST>(B, col, mu, x, vp);
             }
             if (p.writer && warp >= 8) {
                 // the bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition)
@@ -388,16 +428,14 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
             }
             bar_sync_all();                                                            // #4
             if (mine) {
-                seq_rank_one<DP, PART>(B, vp, gdb[which * 2]);
-                if constexpr (PART == 0) asm volatile("cp.async.wait_all;" ::: "memory");
-            }
-            bar_sync_all();                                                            // #4b: the count-table rows landed
-            if (mine) {
+                seq_rank_one<DP, PART, ST>(B, col, vp, gdb[which * 2]);
+                if constexpr (G::TRI) asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's own copies
                 const double *nt = ntb + which * 8;   // r0: CN, G | r1: CN, G, H, BETA, RK
                 if constexpr (G::TRI) {
                     // m' = m -+ d / kappa(n2), d = m - x  (this thread is the only writer of these means)
                     const double *x = xb + jj * DP;
-                    const double rk2 = which ? -nt[6] : nt[6];
+                    const double rk = (PART == 0) ? nt[6] : rkb[which * 2];
+                    const double rk2 = which ? -rk : rk;
 #pragma unroll
                     for (int a = 0; a < G::TN; ++a) {
                         double *pm = col + (Ly::MU + G::O + a) * ST;
