@@ -37,6 +37,7 @@ extern "C" {
 
 #define BGMM_COV_FULL 0 /* NIW, full covariance      -- pybgmm/gaussian/gaussian_components.py      */
 #define BGMM_COV_DIAG 1 /* product of NIX, diagonal  -- pybgmm/gaussian/gaussian_components_diag.py */
+#define BGMM_COV_FIXED 2 /* known diagonal variance  -- pybgmm/gaussian/gaussian_components_fixedvar.py (bgmm_create_fixedvar) */
 
 typedef struct bgmm_handle bgmm_t;
 
@@ -79,6 +80,15 @@ int bgmm_device_count(void);
 int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const double *m0, double k0, int64_t v0,
                 const double *S0, int32_t K_max, const double *lgamma_half_tab, const double *log_tab,
                 int64_t tab_len, int32_t device, bgmm_t **out);
+/*
+ * replaces: GaussianComponentsFixedVar.__init__ + _cache (gaussian_components_fixedvar.py:75-130), prior =
+ * FixedVarPrior(var, mu_0, var_0) (:304-311): components with a known diagonal variance `var` (D) and independent normal
+ * priors N(mu_0, var_0) (D each) on their means; IGMM's covariance_type="fixed" (igmm/igmm.py:108-109).  The handle
+ * behaves like any other: in bgmm_get_state / bgmm_set_component_stats, m_num is mu_N_numerators (K_max x D), S_part is
+ * precision_Ns (K_max x D), logdet is log_prod_precision_preds, inv_covar is precision_preds (K_max x D).
+ */
+int bgmm_create_fixedvar(const double *X, int64_t N, int32_t D, const double *var, const double *mu_0, const double *var_0,
+                         int32_t K_max, int32_t device, bgmm_t **out);
 int bgmm_destroy(bgmm_t *h);
 
 /* All kernels of this handle are enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream). */

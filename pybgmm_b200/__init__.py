@@ -6,9 +6,10 @@ The package layout mirrors the reference's (`pybgmm.prior`, `pybgmm.gaussian`, `
 libbgmm_b200.so (hand-written sm_100a CUDA); there is no CPU fallback.
 """
 from .prior import NIW
-from .gaussian import GaussianComponents, GaussianComponentsDiag
+from .gaussian import GaussianComponents, GaussianComponentsDiag, GaussianComponentsFixedVar, FixedVarPrior
 from .gmm import GMM
 from .igmm import IGMM, CRPMM, PCRPMM, ADAPCRPMM
 
-__all__ = ["NIW", "GaussianComponents", "GaussianComponentsDiag", "GMM", "IGMM", "CRPMM", "PCRPMM", "ADAPCRPMM"]
+__all__ = ["NIW", "FixedVarPrior", "GaussianComponents", "GaussianComponentsDiag", "GaussianComponentsFixedVar", "GMM",
+           "IGMM", "CRPMM", "PCRPMM", "ADAPCRPMM"]
 __version__ = "0.1.0"

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BGMM_B200_LIB", os.path.join(HERE, "lib", "libbgmm_b200.so"))
 
 BGMM_OK, BGMM_EINVAL, BGMM_ENODEV, BGMM_EKMAX, BGMM_ENUMERIC, BGMM_ENOMEM, BGMM_EWATCHDOG = 0, -1, -2, -3, -4, -5, -6
-COV_FULL, COV_DIAG = 0, 1
+COV_FULL, COV_DIAG, COV_FIXED = 0, 1, 2
 
 EXPORTS = (
     "bgmm_set_component_stats",
@@ -21,7 +21,7 @@ EXPORTS = (
     "bgmm_sweep_index", "bgmm_get_state", "bgmm_get_assignments_dev", "bgmm_K", "bgmm_log_prior",
     "bgmm_log_post_pred", "bgmm_log_marg_k", "bgmm_log_marg", "bgmm_add_item", "bgmm_del_item", "bgmm_mt19937_fill",
     "bgmm_set_true_labels", "bgmm_contingency", "bgmm_cluster_ssq", "bgmm_set_label", "bgmm_set_state", "bgmm_set_guard",
-    "bgmm_fork", "bgmm_sweep_many",
+    "bgmm_fork", "bgmm_sweep_many", "bgmm_create_fixedvar",
 )
 
 
@@ -68,6 +68,7 @@ def lib():
     L.bgmm_device_count.restype = C.c_int
     L.bgmm_create.argtypes = [dp, C.c_int64, C.c_int32, C.c_int32, dp, C.c_double, C.c_int64, dp, C.c_int32, dp, dp,
                               C.c_int64, C.c_int32, C.POINTER(vp)]
+    L.bgmm_create_fixedvar.argtypes = [dp, C.c_int64, C.c_int32, dp, dp, dp, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.bgmm_destroy.argtypes = [vp]
     L.bgmm_set_stream.argtypes = [vp, vp]
     L.bgmm_set_assignments.argtypes = [vp, ip]
@@ -162,6 +163,23 @@ class Chain(object):
                                  self.K_max, _dp(lg), _dp(lv), 0 if lg is None else len(lg), int(device), C.byref(h)))
         self._h = h
         self._ss = self.D * self.D if self.cov == COV_FULL else self.D
+
+    @classmethod
+    def fixed_variance(cls, X, var, mu_0, var_0, K_max, device=0):
+        """A chain over fixed-variance components (bgmm_create_fixedvar): known diagonal data variance `var`,
+        independent normal priors N(mu_0, var_0) on the means; var, mu_0, var_0 are D-vectors (or scalars)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise ValueError("X must be a 2-dimensional array.")
+        self = object.__new__(cls)
+        self.N, self.D = X.shape
+        self.cov, self.K_max, self._ss = COV_FIXED, int(K_max), self.D
+        vec = [np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (self.D,))) for v in (var, mu_0, var_0)]
+        h = C.c_void_p()
+        _check(lib().bgmm_create_fixedvar(_dp(X), self.N, self.D, _dp(vec[0]), _dp(vec[1]), _dp(vec[2]), self.K_max,
+                                          int(device), C.byref(h)))
+        self._h = h
+        return self
 
     def fork(self):
         """A new chain on the same data and prior: shares the device copy of X, the cached log prior and the tables

@@ -24,6 +24,7 @@ namespace bgmm {
 
 constexpr int COV_FULL = 0;
 constexpr int COV_DIAG = 1;
+constexpr int COV_FIXED = 2;        // known diagonal variance, normal prior on the means (gaussian_components_fixedvar.py)
 constexpr int T_SWEEP = 256;        // threads per CTA of the sweep kernel
 constexpr int MAX_DIRTY = 8;
 constexpr long long POS_INF = 0x7fffffffffffffffLL;
@@ -36,7 +37,10 @@ enum { SC_C = 0, SC_H = 1, SC_INVNU = 2, SC_LC = 3, SC_N = 4, SC_LOGDET = 5, SC_
 __host__ __device__ constexpr int packed_len(int dp) { return dp * (dp + 1) / 2; }
 __host__ __device__ constexpr int rec_mu_off(int dp, int cov) { return cov == COV_FULL ? packed_len(dp) : 0; }
 __host__ __device__ constexpr int rec_iv_off(int dp) { return dp; }  // diag only
-__host__ __device__ constexpr int rec_sc_off(int dp, int cov) { return cov == COV_FULL ? packed_len(dp) + dp : 2 * dp; }
+// fixed variance: [mean DP][predictive precision DP][precision-weighted sum DP][posterior precision DP][scalars]
+__host__ __device__ constexpr int rec_sc_off(int dp, int cov) {
+    return cov == COV_FULL ? packed_len(dp) + dp : (cov == COV_FIXED ? 4 * dp : 2 * dp);
+}
 __host__ __device__ constexpr int rec_len(int dp, int cov) { return (rec_sc_off(dp, cov) + SC_COUNT + 1) & ~1; }
 __host__ __device__ constexpr int stat_len(int dp, int cov) { return cov == COV_FULL ? packed_len(dp) : dp; }
 // column-major packed lower triangle (record): element (a,b), a >= b
@@ -78,6 +82,7 @@ struct Ctl {
     long long watchdog_ns;         // spin loops give up (error word + trap) after this many ns of the global timer
     long long prof[16];            // phase clocks of CTA 0 (cycles), see bgmm_fast.cuh
     unsigned long long wsum[16], wcnt[16], wmax[16];  // evaluator unit clocks by category (profile builds)
+    long long tprof[4][16];        // register step: cycles per (part, phase) of warps 0 / 4 / 8 / 12 (profile builds)
 };
 
 struct Params {
@@ -101,8 +106,9 @@ struct Params {
     double *wbuf;             // grid x (K_max+1) x T scratch
     Ctl *ctl;
     // prior (pybgmm/prior/niw.py:10-23)
-    const double *m0;         // DP
-    const double *S0;         // SS
+    const double *m0;         // DP   (fixed variance: mu_0)
+    const double *S0;         // SS   (fixed variance: the prior precision of the means, 1 / var_0)
+    const double *tau;        // fixed variance only: the data precision 1 / var (DP)
     double k0;
     long long v0;
     // sizes
@@ -265,6 +271,17 @@ __device__ __forceinline__ double lpp_other(const double *__restrict__ rec, cons
     if (COV == COV_FULL) {
         const double q = quad_full<DP, CG>(rec, x);
         return c - h * log(1.0 + inv_nu * q);
+    } else if (COV == COV_FIXED) {
+        // product of normals (gaussian_components_fixedvar.py:221-232): c = -D/2 log 2 pi + sum log(pred) / 2
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < DP; ++a) {
+            if (a < D) {
+                const double dl = ldr<CG>(rec + a) - x[a];
+                s += (dl * dl) * ldr<CG>(rec + DP + a);
+            }
+        }
+        return c - 0.5 * s;
     } else {
         const double s = logsum_diag<DP, CG>(rec, x, D, inv_nu);
         return c - h * s;
@@ -290,6 +307,25 @@ __device__ __forceinline__ double weight_own_removed(const double *__restrict__ 
                                                      const Params &p, bool *ok) {
     constexpr int SO = rec_sc_off(DP, COV);
     const int D = p.D;
+    if (COV == COV_FIXED) {
+        // the reference's own del_item arithmetic on the component's statistics (gaussian_components_fixedvar.py:
+        // 164-180, :278-286), evaluated on the fly: nothing to factor, so no closed form is needed
+        const double n1 = ldr<CG>(rec + SO + SC_N) - 1.0;
+        double lp = 0.0, s = 0.0;
+#pragma unroll
+        for (int a = 0; a < DP; ++a) {
+            if (a < D) {
+                const double ta = p.tau[a];
+                const double num1 = __dsub_rn(ldr<CG>(rec + 2 * DP + a), __dmul_rn(ta, x[a]));
+                const double t1 = __dsub_rn(ldr<CG>(rec + 3 * DP + a), ta);
+                const double pred = t1 * ta / (t1 + ta);
+                const double dl = num1 / t1 - x[a];
+                lp += log(pred);
+                s += (dl * dl) * pred;
+            }
+        }
+        return log_count(n1, p.power) + ((-0.5 * D * log(2.0 * M_PI) + 0.5 * lp) - 0.5 * s);
+    }
     const double n = ldr<CG>(rec + SO + SC_N);
     const double f = ldr<CG>(rec + SO + SC_F);
     const double ld = ldr<CG>(rec + SO + SC_LOGDET);
@@ -401,6 +437,27 @@ __device__ bool refactor_warp(const Params &p, const double *num, const double *
                 put(off + (a - b), v);
             }
         }
+    } else if (COV == COV_FIXED) {
+        // predictive precision tau_N tau / (tau_N + tau), its log product (gaussian_components_fixedvar.py:278-286);
+        // the prior alone: precision 1 / var_0 (:204-210)
+        nu = 0; f = 0.0;
+        double lp = 0.0;
+        for (int a = 0; a < D; ++a) {
+            double pred, tn = 0.0, nm = 0.0;
+            if (mode == 0) {
+                tn = __ldcg(S + a);
+                nm = __ldcg(num + a);
+                pred = tn * p.tau[a] / (tn + p.tau[a]);
+            } else {
+                pred = p.S0[a];
+            }
+            if (!(pred > 0.0) || !(pred < 1e300)) bad = true;
+            lp += log(pred);
+            if (lane == 0) { put(DP + a, pred); put(2 * DP + a, nm); put(3 * DP + a, tn); }
+        }
+        if (bad) return false;
+        logdet = lp;
+        for (int a = D + lane; a < DP; a += 32) { put(DP + a, 0.0); put(2 * DP + a, 0.0); put(3 * DP + a, 0.0); }
     } else {
         nu = p.v0 + n_cnt;
         f = (kap + 1.) / (kap * vN);
@@ -424,7 +481,10 @@ __device__ bool refactor_warp(const Params &p, const double *num, const double *
     }
     for (int a = lane; a < DP; a += 32) {
         double m = 0.0;
-        if (a < D) m = (mode == 0) ? __ldcg(num + a) / kap : p.m0[a];
+        if (a < D) {
+            if (COV == COV_FIXED) m = (mode == 0) ? __ldcg(num + a) / __ldcg(S + a) : p.m0[a];
+            else m = (mode == 0) ? __ldcg(num + a) / kap : p.m0[a];
+        }
         put(MU + a, m);
     }
     if (lane == 0) {
@@ -432,6 +492,10 @@ __device__ bool refactor_warp(const Params &p, const double *num, const double *
         if (COV == COV_FULL) {
             c = t_const_full(p.lgam, p.logv, nu, D, p.log_pi, logdet);
             h = (nu + D) / 2.;
+        } else if (COV == COV_FIXED) {
+            c = -0.5 * D * log(2.0 * M_PI) + 0.5 * logdet;
+            h = 0.0;
+            nu = 1;
         } else {
             c = t_const_diag(p.lgam, p.logv, nu, D, p.log_pi, logdet);
             h = (nu + 1) / 2.;

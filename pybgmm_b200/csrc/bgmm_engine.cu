@@ -37,6 +37,17 @@ __global__ void k_build_stats(const Params p, const long long *__restrict__ idx,
             else { is_num = true; a = b = e - D; }
         }
         double acc;
+        if (COV == COV_FIXED) {
+            // gaussian_components_fixedvar.py:155-158: precision_0 * mu_0 (+= precision * x), precision_0 (+= precision)
+            acc = is_num ? __dmul_rn(p.S0[a], p.m0[a]) : p.S0[a];
+            for (long long t = lo; t < hi; ++t) {
+                if (is_num) acc = __dadd_rn(acc, __dmul_rn(p.tau[a], p.X[(size_t)idx[t] * DP + a]));
+                else acc = __dadd_rn(acc, p.tau[a]);
+            }
+            if (is_num) p.num[(size_t)k * DP + a] = acc;
+            else p.S[(size_t)k * SS + a] = acc;
+            continue;
+        }
         if (is_num) acc = __dmul_rn(p.k0, p.m0[a]);
         else acc = __dadd_rn(p.S0[COV == COV_FULL ? row_idx(a, b) : a], __dmul_rn(p.k0, __dmul_rn(p.m0[a], p.m0[b])));
         for (long long t = lo; t < hi; ++t) {
@@ -203,6 +214,56 @@ __global__ void k_log_marg_k(const Params p, int DP, double logdet_S0, double *_
     }
 }
 
+// log_marg_k of the fixed-variance components (gaussian_components_fixedvar.py:234-256, Murphy's bayesGauss (55)): the
+// formula needs sum x and sum x^2 over the component's members, which are not part of its statistics, so block k makes
+// one pass over the labels (8 dimensions at a time, register accumulators, a deterministic tree over the block).
+__global__ void k_fixed_log_marg_k(const Params p, int DP, double *__restrict__ out) {
+    __shared__ double red[256];
+    const int k = blockIdx.x, tid = threadIdx.x;
+    const int D = p.D;
+    const double n = (double)p.counts[k];
+    double total = 0.0;
+    for (int a0 = 0; a0 < D; a0 += 8) {
+        double sx[8], sxx[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sx[t] = sxx[t] = 0.0;
+        for (long long i = tid; i < p.N; i += blockDim.x) {
+            const int uid = p.z_uid[i];
+            if (uid < 0 || p.slot_of_uid[uid] != k) continue;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (a0 + t < D) {
+                    const double x = p.X[(size_t)i * DP + a0 + t];
+                    sx[t] += x;
+                    sxx[t] += x * x;
+                }
+            }
+        }
+        for (int t = 0; t < 8 && a0 + t < D; ++t) {
+            double v[2] = {sx[t], sxx[t]};
+            for (int w = 0; w < 2; ++w) {
+                red[tid] = v[w];
+                __syncthreads();
+                for (int o = 128; o >= 1; o >>= 1) {
+                    if (tid < o) red[tid] += red[tid + o];
+                    __syncthreads();
+                }
+                v[w] = red[0];
+                __syncthreads();
+            }
+            if (tid == 0) {
+                const int a = a0 + t;
+                const double tau = p.tau[a], tau0 = p.S0[a], mu0 = p.m0[a];
+                const double s = n / tau0 + 1. / tau;
+                total += (n - 1) / 2. * log(tau) - 0.5 * n * log(2 * M_PI) - 0.5 * log(s) - 0.5 * tau * v[1] -
+                         0.5 * tau0 * (mu0 * mu0) +
+                         0.5 * ((v[0] * v[0]) * tau / tau0 + (mu0 * mu0) * tau0 / tau + 2 * v[0] * mu0) / s;
+            }
+        }
+    }
+    if (tid == 0) out[k] = total;
+}
+
 // inv_covars / logdet_covars views (gaussian_components.py:88-89) reconstructed from the Cholesky record:
 // inv = L^-T L^-1.  One warp per component; W (D x D) in shared memory.
 template <int COV>
@@ -213,7 +274,7 @@ __global__ void k_inv_covar(const Params p, int DP, double *__restrict__ logdet_
     const int R = rec_len(DP, COV);
     const double *rec = p.rec + (size_t)k * R;
     if (lane == 0) logdet_out[k] = rec[rec_sc_off(DP, COV) + SC_LOGDET];
-    if (COV == COV_DIAG) {
+    if (COV != COV_FULL) {   // diag: inv_vars; fixed variance: precision_preds
         for (int a = lane; a < D; a += 32) inv_out[(size_t)k * D + a] = rec[DP + a];
         return;
     }
@@ -250,12 +311,12 @@ static int pad_dim(int D) {
 }
 
 // one getter per instantiation unit (csrc/inst/*.cu, generated); BGMM_HAVE_D<dp> says which were built
-#define DECL(dp) const Ops *bgmm_ops_full_##dp(int (**prep)(bgmm_handle *)); const Ops *bgmm_ops_diag_##dp(int (**prep)(bgmm_handle *));
+#define DECL(dp) const Ops *bgmm_ops_full_##dp(int (**prep)(bgmm_handle *)); const Ops *bgmm_ops_diag_##dp(int (**prep)(bgmm_handle *)); const Ops *bgmm_ops_fixed_##dp(int (**prep)(bgmm_handle *));
 DECL(1) DECL(2) DECL(4) DECL(8) DECL(16) DECL(32) DECL(64)
 #undef DECL
 static const Ops *pick_ops(int cov, int DP, int (**prep)(bgmm_handle *)) {
     switch (DP) {
-#define CASE(dp) case dp: return cov == BGMM_COV_FULL ? bgmm_ops_full_##dp(prep) : bgmm_ops_diag_##dp(prep);
+#define CASE(dp) case dp: return cov == BGMM_COV_FULL ? bgmm_ops_full_##dp(prep) : (cov == BGMM_COV_DIAG ? bgmm_ops_diag_##dp(prep) : bgmm_ops_fixed_##dp(prep));
 #ifdef BGMM_HAVE_D1
         CASE(1)
 #endif
@@ -293,7 +354,7 @@ static void free_all(bgmm_handle *h) {
     if (h->sb && --h->sb->refs == 0) {
         SharedBufs *b = h->sb;
         cudaFree(b->dX); cudaFree(b->d_log_prior); cudaFree(b->d_lgam); cudaFree(b->d_logv); cudaFree(b->d_m0);
-        cudaFree(b->d_S0); cudaFree(b->d_ntab); cudaFree(b->d_fmtab);
+        cudaFree(b->d_S0); cudaFree(b->d_ntab); cudaFree(b->d_fmtab); cudaFree(b->d_tau);
         delete b;
     }
     h->sb = nullptr;
@@ -379,15 +440,21 @@ int bgmm_device_count(void) {
     return n;
 }
 
-int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const double *m0, double k0, int64_t v0,
-                const double *S0, int32_t K_max, const double *lgamma_half_tab, const double *log_tab, int64_t tab_len,
-                int32_t device, bgmm_t **out) {
+}  // extern "C"
+
+// bgmm_create and bgmm_create_fixedvar: var_fixed is the known data variance of the fixed-variance components (then m0 =
+// mu_0, S0 = var_0, and k0 / v0 are not used) and NULL otherwise
+static int create_impl(const double *X, int64_t N, int32_t D, int32_t cov_type, const double *m0, double k0, int64_t v0,
+                       const double *S0, const double *var_fixed, int32_t K_max, const double *lgamma_half_tab,
+                       const double *log_tab, int64_t tab_len, int32_t device, bgmm_t **out) {
     if (!out) return fail(BGMM_EINVAL, "out is NULL");
     *out = nullptr;
     if (!X || !m0 || !S0) return fail(BGMM_EINVAL, "X, m0, S0 must not be NULL");
     if (N < 1 || D < 1) return fail(BGMM_EINVAL, "N and D must be >= 1");
     if (D > 64) return fail(BGMM_EINVAL, "D > 64 is not supported by this build");
-    if (cov_type != BGMM_COV_FULL && cov_type != BGMM_COV_DIAG) return fail(BGMM_EINVAL, "invalid covariance type");
+    if (cov_type != BGMM_COV_FULL && cov_type != BGMM_COV_DIAG && cov_type != BGMM_COV_FIXED)
+        return fail(BGMM_EINVAL, "invalid covariance type");
+    if ((cov_type == BGMM_COV_FIXED) != (var_fixed != nullptr)) return fail(BGMM_EINVAL, "invalid covariance type");
     if (v0 < D) return fail(BGMM_EINVAL, "v_0 must be >= D (prior/niw.py:21)");
     if (!(k0 > 0.0)) return fail(BGMM_EINVAL, "k_0 must be > 0");
     if (K_max < 1 || K_max > 4096) return fail(BGMM_EINVAL, "K_max must be in [1, 4096]");
@@ -436,6 +503,14 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
             }
         }
         h->logdet_S0 = ld;
+    } else if (cov_type == BGMM_COV_FIXED) {
+        // precision = 1 / var, precision_0 = 1 / var_0   (gaussian_components_fixedvar.py:80-82)
+        h->tauv.assign(DP, 0.0);
+        for (int a = 0; a < D; ++a) {
+            if (!(S0[a] > 0.0) || !(var_fixed[a] > 0.0)) { delete h; return fail(BGMM_ENUMERIC, "var and var_0 must be positive"); }
+            h->S0p[a] = 1. / S0[a];
+            h->tauv[a] = 1. / var_fixed[a];
+        }
     } else {
         double ld = 0.0;
         for (int a = 0; a < D; ++a) {
@@ -476,9 +551,11 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
     ALLOC(b->d_logv, sizeof(double) * (size_t)need);
     ALLOC(b->d_m0, sizeof(double) * DP);
     ALLOC(b->d_S0, sizeof(double) * SS);
+    if (cov_type == BGMM_COV_FIXED) ALLOC(b->d_tau, sizeof(double) * DP);
 #undef ALLOC
     h->dX = b->dX; h->d_log_prior = b->d_log_prior; h->d_lgam = b->d_lgam; h->d_logv = b->d_logv;
-    h->d_m0 = b->d_m0; h->d_S0 = b->d_S0;
+    h->d_m0 = b->d_m0; h->d_S0 = b->d_S0; h->d_tau = b->d_tau;
+    if (b->d_tau) CU(cudaMemcpy(b->d_tau, h->tauv.data(), sizeof(double) * DP, cudaMemcpyHostToDevice));
     if (int rc = h->ops->fast_setup(h)) { free_all(h); delete h; return rc; }
     if (int rc = alloc_chain_state(h)) { free_all(h); delete h; return rc; }
 
@@ -513,6 +590,21 @@ int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const d
     return 0;
 }
 
+extern "C" {
+
+int bgmm_create(const double *X, int64_t N, int32_t D, int32_t cov_type, const double *m0, double k0, int64_t v0,
+                const double *S0, int32_t K_max, const double *lgamma_half_tab, const double *log_tab, int64_t tab_len,
+                int32_t device, bgmm_t **out) {
+    if (cov_type != BGMM_COV_FULL && cov_type != BGMM_COV_DIAG) return fail(BGMM_EINVAL, "invalid covariance type");
+    return create_impl(X, N, D, cov_type, m0, k0, v0, S0, nullptr, K_max, lgamma_half_tab, log_tab, tab_len, device, out);
+}
+
+int bgmm_create_fixedvar(const double *X, int64_t N, int32_t D, const double *var, const double *mu_0, const double *var_0,
+                         int32_t K_max, int32_t device, bgmm_t **out) {
+    if (!var) return fail(BGMM_EINVAL, "var must not be NULL");
+    return create_impl(X, N, D, BGMM_COV_FIXED, mu_0, 1.0, D, var_0, var, K_max, nullptr, nullptr, 0, device, out);
+}
+
 int bgmm_fork(bgmm_t *parent, bgmm_t **out) {
     if (!parent || !out) return fail(BGMM_EINVAL, "NULL argument");
     *out = nullptr;
@@ -528,7 +620,7 @@ int bgmm_fork(bgmm_t *parent, bgmm_t **out) {
     h->sb->refs += 1;
     SharedBufs *b = h->sb;
     h->dX = b->dX; h->d_log_prior = b->d_log_prior; h->d_lgam = b->d_lgam; h->d_logv = b->d_logv;
-    h->d_m0 = b->d_m0; h->d_S0 = b->d_S0;
+    h->d_m0 = b->d_m0; h->d_S0 = b->d_S0; h->d_tau = b->d_tau;
     if (int rc = h->ops->fast_setup(h)) { free_all(h); delete h; return rc; }
     if (int rc = alloc_chain_state(h)) { free_all(h); delete h; return rc; }
     // the prior's generic record (bgmm_log_prior's source) is per handle: copy the parent's
@@ -636,7 +728,8 @@ int bgmm_set_assignments(bgmm_t *h, const int64_t *z) {
     Params p = make_params(h);
     if (K0 > 0) {
         if (h->cov == BGMM_COV_FULL) k_build_stats<COV_FULL><<<K0, 256, 0, st>>>(p, d_idx, d_start, DP);
-        else k_build_stats<COV_DIAG><<<K0, 256, 0, st>>>(p, d_idx, d_start, DP);
+        else if (h->cov == BGMM_COV_DIAG) k_build_stats<COV_DIAG><<<K0, 256, 0, st>>>(p, d_idx, d_start, DP);
+        else k_build_stats<COV_FIXED><<<K0, 256, 0, st>>>(p, d_idx, d_start, DP);
         CU(cudaGetLastError());
         if (int rc = h->ops->refactor_all(h, p, 0, K0)) return rc;
     }
@@ -669,6 +762,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     c.watchdog_ns = h->watchdog_ns;
     memset(c.prof, 0, sizeof(c.prof));
     memset(c.wsum, 0, sizeof(c.wsum)); memset(c.wcnt, 0, sizeof(c.wcnt)); memset(c.wmax, 0, sizeof(c.wmax));
+    memset(c.tprof, 0, sizeof(c.tprof));
     const double one = 1.0;
     memcpy(&c.margin_bits, &one, 8);
     c.error = 0; c.bar_count = 0; c.rb_count = 0; c.rb_word = 0; c.pos = 0; c.win = 0; c.first = POS_INF; c.n_dirty = 0;
@@ -749,6 +843,13 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         out->explicit_evals = c.explicit_evals; out->refreshes = c.refreshes; out->generic_from = generic_from;
         for (int t = 0; t < 16; ++t) out->phase_cycles[t] = c.prof[t];
         if (getenv("BGMM_WPROF")) {
+            static const char *tn[11] = {"stage", "A", "wait1", "finish+scan", "wait2", "draw", "wait3", "move-a", "wait4",
+                                         "move-b", "wait5"};
+            for (int pt = 0; pt < 4; ++pt) {
+                fprintf(stderr, "  seq timeline part %d:", pt);
+                for (int t = 0; t < 11; ++t) fprintf(stderr, " %s=%lld", tn[t], c.tprof[pt][t]);
+                fprintf(stderr, "\n");
+            }
             static const char *nm[16] = {"idle", "load", "chunk", "rowup", "stay", "cand", "full", "pick",
                                          "w-chunk", "w-patchN", "w-patch2", "w-none", "", "", "", ""};
             for (int t = 0; t < 16; ++t)
@@ -986,7 +1087,8 @@ int bgmm_get_state(bgmm_t *h, int64_t *z, int64_t *counts, int32_t *K, double *m
             CU(cudaMalloc((void **)&d_inv, sizeof(double) * (size_t)Kl * ssr));
             Params p = make_params(h);
             if (h->cov == BGMM_COV_FULL) k_inv_covar<COV_FULL><<<Kl, 32, sizeof(double) * D * D, st>>>(p, DP, d_ld, d_inv);
-            else k_inv_covar<COV_DIAG><<<Kl, 32, 0, st>>>(p, DP, d_ld, d_inv);
+            else if (h->cov == BGMM_COV_DIAG) k_inv_covar<COV_DIAG><<<Kl, 32, 0, st>>>(p, DP, d_ld, d_inv);
+            else k_inv_covar<COV_FIXED><<<Kl, 32, 0, st>>>(p, DP, d_ld, d_inv);
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(ld.data(), d_ld, sizeof(double) * Kl, cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(iv.data(), d_inv, sizeof(double) * (size_t)Kl * ssr, cudaMemcpyDeviceToHost, st));
@@ -1048,8 +1150,10 @@ int bgmm_log_marg_k(bgmm_t *h, double *out) {
     Params p = make_params(h);
     if (h->cov == BGMM_COV_FULL)
         k_log_marg_k<COV_FULL><<<h->K, 32, sizeof(double) * (packed_len(h->D) + 2), st>>>(p, h->DP, h->logdet_S0, d_out);
-    else
+    else if (h->cov == BGMM_COV_DIAG)
         k_log_marg_k<COV_DIAG><<<h->K, 32, 16, st>>>(p, h->DP, h->logdet_S0, d_out);
+    else
+        k_fixed_log_marg_k<<<h->K, 256, 0, st>>>(p, h->DP, d_out);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, d_out, sizeof(double) * h->K, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1128,6 +1232,8 @@ int bgmm_contingency(bgmm_t *h, int64_t *table) {
 
 int bgmm_cluster_ssq(bgmm_t *h, double *out) {
     if (!h || !out) return fail(BGMM_EINVAL, "NULL argument");
+    if (h->cov == BGMM_COV_FIXED)
+        return fail(BGMM_EINVAL, "the fixed-variance statistics do not hold sum x^2: count the loss from the labels");
     if (h->K == 0) return 0;
     CU(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;

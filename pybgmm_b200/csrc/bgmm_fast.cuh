@@ -177,6 +177,7 @@ struct FSh {
     double wtot[4], wmg[4];
     int wcand[4];
     long long prof[PH_COUNT], prof_last;
+    long long tprof[4][16];   // bgmm_seq.cuh timeline (profile builds)
 };
 
 // The per-round barrier.  Arrival is one acq_rel atomic (its release orders this CTA's candidate publication, made
@@ -1815,6 +1816,7 @@ __device__ __forceinline__ void fast_sweep_body(const Params &p_in) {
         sh.ver = 1; sh.dall_ver = 1;
         for (int t = 0; t < DLOG; ++t) sh.dlog_a[t] = sh.dlog_b[t] = -1;
         for (int t = 0; t < PH_COUNT; ++t) sh.prof[t] = 0;
+        for (int t = 0; t < 64; ++t) (&sh.tprof[0][0])[t] = 0;
         sh.prof_last = clock64();
         sh.mode = (p.engine == 2) ? 1 : ((p.engine == 1) ? 0 : (p.init_gap >= (double)p.gap_to_win ? 1 : 0));
         if (p.solo) sh.mode = 0;
@@ -1934,6 +1936,7 @@ __device__ __forceinline__ void fast_sweep_body(const Params &p_in) {
             atomicMin(&ctl->margin_bits, sh.margin_bits);
             __stcg(&ctl->gap, sh.gap);
             for (int t = 0; t < PH_COUNT; ++t) __stcg(&ctl->prof[t], sh.prof[t]);
+            for (int t = 0; t < 64; ++t) __stcg(&ctl->tprof[0][0] + t, (&sh.tprof[0][0])[t]);
         }
     }
 }

@@ -30,6 +30,23 @@ namespace fast {
 
 constexpr int SEQ_KMAX = 128;   // the K + 1 choices sit one per thread in warps 0..3
 
+// profile builds: a timeline of the step for the first warp of each part (lane 0 of warps 0, 4, 8, 12): cycles from the
+// previous mark to this one, summed per (part, phase) in FSh::tprof
+#ifdef BGMM_PROFILE
+#define SEQ_T(idx)                                                         \
+    do {                                                                   \
+        if (lane == 0 && (warp & 3) == 0) {                                \
+            const long long t_ = clock64();                                \
+            sh.tprof[warp >> 2][idx] += t_ - tlast_;                       \
+            tlast_ = t_;                                                   \
+        }                                                                  \
+    } while (0)
+#define SEQ_T_DECL() long long tlast_ = clock64()
+#else
+#define SEQ_T(idx) do { } while (0)
+#define SEQ_T_DECL() do { } while (0)
+#endif
+
 // geometry of block PART of the symmetric DP x DP matrix B (packed lower triangle, row-major: e = a (a + 1) / 2 + b)
 //   L = [0, H), U = [H, DP);  part 0: triangle LL, part 1: triangle UU, part 2 / 3: rows [R0, R0 + RN) of the block UL
 template <int DP, int PART> struct Blk {
@@ -262,6 +279,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     double B[G::NEA];
     B[0] = 0.0;
     seq_load_block<DP, PART, ST>(col, B);
+    SEQ_T_DECL();
 
     while (true) {
         const long long pos = sh.pos;
@@ -286,6 +304,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
         }
         bar_sync_all();
         F_PROF(PH_STAGE);
+        SEQ_T(0);   // staging + loop control
         int K = sh.K;
         int done = 0;
         for (int jj = 0; jj < nb; ++jj) {
@@ -299,7 +318,9 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                 double pq = 0.0;
                 if (k < K) pq = seq_quad_part<DP, PART, ST>(B, col, mu, x);
                 if constexpr (PART > 0) psum[(PART - 1) * SEQ_KMAX + k] = pq;
+                SEQ_T(1);   // head + phase A
                 bar_sync_all();                                                        // #1
+                SEQ_T(2);   // wait at #1
                 if constexpr (PART == 0) {
                     // ---- finish the K + 1 weights, scan them, draw (crpmm.py:68-78, utils.py:7-20) ----
                     const double wref = p.log_alpha + lpb[jj];   // the new-table weight (crpmm.py:74) is the exp scale
@@ -321,7 +342,9 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                         if (lane >= o) incl += t;
                     }
                     if (lane == 31) sh.wtot[warp] = incl;
+                    SEQ_T(3);   // finish + scan
                     bar_sync_front();                                                  // #2 (warps 0..3)
+                    SEQ_T(4);   // wait at #2
                     const double w0 = sh.wtot[0], w1 = sh.wtot[1], w2 = sh.wtot[2], w3 = sh.wtot[3];
                     const double p1 = w0, p2 = w0 + w1, p3 = p2 + w2, tot = p3 + w3;
                     const double t0 = ub[jj] * tot;
@@ -342,7 +365,9 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                         if (!(tot > 0.0) || !(tot < INFINITY)) sh.rare_seq = seq;
                     }
                 }
+                SEQ_T(5);   // draw
                 bar_sync_all();                                                        // #3
+                SEQ_T(6);   // wait at #3
                 F_PROF(PH_EVAL);
                 k_new = sh.k_new;
                 const double mg = sh.last_mg;
@@ -426,7 +451,9 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                     if (tid == 384) __stcg(p.z_out + ib[jj], s.uid_of_slot[k_new]);
                 }
             }
+            SEQ_T(7);   // decision + first half of the move
             bar_sync_all();                                                            // #4
+            SEQ_T(8);   // wait at #4
             if (mine) {
                 seq_rank_one<DP, PART, ST>(B, col, vp, gdb[which * 2]);
                 if constexpr (G::TRI) asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's own copies
@@ -459,7 +486,9 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                     if (which == 1) sh.moves += 1;
                 }
             }
+            SEQ_T(9);   // second half of the move
             bar_sync_all();                                                            // #5
+            SEQ_T(10);  // wait at #5
             F_PROF(PH_UPDATE);
             F_COUNT(PH_MOVES);
             const bool ra = (sh.refresh_a == seq), rb = (sh.refresh_b == seq);

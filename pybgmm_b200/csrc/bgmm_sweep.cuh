@@ -100,6 +100,16 @@ template <int DP, int COV> __device__ void stats_axpy(const Params &p, int slot,
     const int D = p.D;
     double *num = p.num + (size_t)slot * DP;
     double *S = p.S + (size_t)slot * SS;
+    if (COV == COV_FIXED) {
+        // mu_N_numerators +-= precision * X[i]; precision_Ns +-= precision   (gaussian_components_fixedvar.py:157-158, :177-178)
+        for (int a = threadIdx.x; a < D; a += blockDim.x) {
+            const double tx = __dmul_rn(p.tau[a], x[a]);
+            const double v = __ldcg(num + a), t = __ldcg(S + a);
+            __stcg(num + a, sign > 0 ? __dadd_rn(v, tx) : __dsub_rn(v, tx));
+            __stcg(S + a, sign > 0 ? __dadd_rn(t, p.tau[a]) : __dsub_rn(t, p.tau[a]));
+        }
+        return;
+    }
     for (int a = threadIdx.x; a < D; a += blockDim.x) {
         const double v = __ldcg(num + a);
         __stcg(num + a, sign > 0 ? __dadd_rn(v, x[a]) : __dsub_rn(v, x[a]));
@@ -128,6 +138,13 @@ template <int DP, int COV> __device__ void stats_init_prior(const Params &p, int
     const int D = p.D;
     double *num = p.num + (size_t)slot * DP;
     double *S = p.S + (size_t)slot * SS;
+    if (COV == COV_FIXED) {   // precision_0 * mu_0, precision_0   (gaussian_components_fixedvar.py:155-156)
+        for (int a = threadIdx.x; a < DP; a += blockDim.x) {
+            __stcg(num + a, a < D ? __dmul_rn(p.S0[a], p.m0[a]) : 0.0);
+            __stcg(S + a, a < D ? p.S0[a] : 0.0);
+        }
+        return;
+    }
     for (int a = threadIdx.x; a < DP; a += blockDim.x) __stcg(num + a, a < D ? __dmul_rn(p.k0, p.m0[a]) : 0.0);
     if (COV == COV_FULL) {
         const int P = packed_len(D);

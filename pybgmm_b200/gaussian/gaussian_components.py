@@ -61,8 +61,7 @@ class _DeviceComponents(object):
                               "explicitly" % (DEFAULT_K_MAX, self.N), stacklevel=3)
         self.K_max = int(K_max)
         self._check_prior()
-        self._chain = _lib.Chain(X, prior.m_0, prior.k_0, prior.v_0, prior.S_0, self.K_max,
-                                 covariance_type=self._COV, device=device)
+        self._chain = self._make_chain(X, device)
         self._cache = None
         self._labels = None
         self._counts = None
@@ -84,6 +83,11 @@ class _DeviceComponents(object):
 
     def _check_prior(self):
         assert np.asarray(self.prior.S_0).shape == (self.D, self.D)
+
+    def _make_chain(self, X, device):
+        prior = self.prior
+        return _lib.Chain(X, prior.m_0, prior.k_0, prior.v_0, prior.S_0, self.K_max, covariance_type=self._COV,
+                          device=device)
 
     # ---- lazily synchronised views ------------------------------------------------------------
     def _state(self):

@@ -40,8 +40,11 @@ class GMM(object):
                 table = None          # unassigned data form a cluster of their own in the reference: count on the host
         if table is not None:
             table = table[:, :-1]
-            loss = utils.cluster_loss_from_ssq(comps.cluster_ssq())
             z = None
+            try:
+                loss = utils.cluster_loss_from_ssq(comps.cluster_ssq())
+            except NotImplementedError:   # fixed-variance statistics hold no sum of squares: count from the labels
+                loss = utils.cluster_loss_inertia(comps.X, comps.assignments)
         else:
             z = comps.assignments
             loss = utils.cluster_loss_inertia(comps.X, z)

@@ -8,7 +8,7 @@ from scipy import stats
 from scipy.special import gammaln
 
 from .. import _lib
-from ..gaussian import GaussianComponents, GaussianComponentsDiag
+from ..gaussian import GaussianComponents, GaussianComponentsDiag, GaussianComponentsFixedVar
 from ..gmm import GMM
 
 logger = logging.getLogger(__name__)
@@ -27,9 +27,9 @@ class IGMM(GMM):
         self.alpha = alpha
         self.save_path = save_path
         z0 = self._initial_assignments(assignments, K)
-        component_classes = {"full": GaussianComponents, "diag": GaussianComponentsDiag}
-        if covariance_type == "fixed":
-            raise NotImplementedError("fixed-variance components are not on the accelerated path (SURVEY.md 8f)")
+        # igmm.py:104-111: "full" -> NIW components, "diag" -> product of NIX, "fixed" -> known variance
+        component_classes = {"full": GaussianComponents, "diag": GaussianComponentsDiag,
+                             "fixed": GaussianComponentsFixedVar}
         assert covariance_type in component_classes, "Invalid covariance type."
         self.components = component_classes[covariance_type](X, kernel_prior, z0, K_max, device=device)
         self.last_sweep_stats = None
