@@ -35,9 +35,9 @@ constexpr int SEQ_KMAX = 128;   // the K + 1 choices sit one per thread in warps
 #ifdef BGMM_PROFILE
 #define SEQ_T(idx)                                                         \
     do {                                                                   \
-        if (lane == 0 && (warp & 3) == 0) {                                \
+        if (lane == 0 && grp == 0) {                                       \
             const long long t_ = clock64();                                \
-            sh.tprof[warp >> 2][idx] += t_ - tlast_;                       \
+            sh.tprof[PART][idx] += t_ - tlast_;                       \
             tlast_ = t_;                                                   \
         }                                                                  \
     } while (0)
@@ -62,7 +62,7 @@ template <int DP, int PART> struct Blk {
     // of the block's NE elements the first NR (in the block's own packed order) live in registers, the rest stay in
     // the shared-memory record: 24 doubles + the step's working set fit the 128-register budget of a 512-thread CTA
     // without spilling (local memory has almost no L1 here -- shared memory takes ~220 KB of the SM's 256 KB)
-    static constexpr int RCAP = 24;
+    static constexpr int RCAP = PART == 0 ? 20 : 24;
     static constexpr int NR = NE > RCAP ? RCAP : NE;
     static constexpr int NEA = NR > 0 ? NR : 1;
     // local packed index / global packed index (row-major lower triangle of the DP x DP matrix) of element (a, b)
@@ -73,6 +73,13 @@ template <int DP, int PART> struct Blk {
     static constexpr int TNA = TN > 0 ? TN : 1;
     static constexpr int RNA = RN > 0 ? RN : 1;
 };
+
+// Warp w runs on scheduler w % 4.  The four parts are four different instruction streams (the block geometry is
+// compile-time), and a scheduler that hosts a warp of every part would keep four streams in its instruction cache;
+// with this mapping every scheduler hosts two parts (two warps of each): schedulers 0, 1 the triangles, 2, 3 the
+// rectangles.  The four warps of a part hold the component groups 0..3 (32 components each).
+__device__ __forceinline__ int seq_part_of_warp(int w) { return ((w & 3) >> 1) * 2 + ((w >> 2) & 1); }
+__device__ __forceinline__ int seq_group_of_warp(int w) { return (w & 1) * 2 + (w >> 3); }
 
 __device__ __forceinline__ void bar_sync_all() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_front() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // warps 0..3
@@ -242,6 +249,27 @@ __device__ __forceinline__ void seq_rank_one(double (&B)[Blk<DP, PART>::NEA], do
     }
 }
 
+// 1 / a for a > 0 (normal range) without a division: single-precision seed, three Newton steps (~1 ulp)
+__device__ __forceinline__ double seq_recip(double a) {
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)a));
+    double r = (double)rf;
+    r = fma(r, fma(-a, r, 1.0), r);
+    r = fma(r, fma(-a, r, 1.0), r);
+    r = fma(r, fma(-a, r, 1.0), r);
+    return r;
+}
+// count-table rows n2 - 1 and n2 (n2 = n + 1: the datum joins; n2 = n - 1 with `leave`) into 8 doubles of shared
+// memory, asynchronously: dst = [r0.CN, r0.G, r1.CN, r1.G, r1.H, r1.BETA, r1.RK, -]
+__device__ __forceinline__ void seq_fetch_rows(const double *ntab, long long n_cur, double *dst_sh, bool leave = false) {
+    const double *r0 = ntab + (size_t)(n_cur + (leave ? -2 : 0)) * NT_W;
+    const uint32_t dst = smem_u32(dst_sh);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(r0) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(r0 + NT_W) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 32), "l"(r0 + NT_W + 2) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 48), "l"(r0 + NT_W + 4) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Sequential batches with the B blocks in registers, for the warps of part PART.  Every warp of the CTA calls its own
 // instantiation; all take the same (CTA-uniform) decisions and meet at the same barriers.  Returns when the sweep is
@@ -263,15 +291,18 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     const long long *ib = reinterpret_cast<const long long *>(smem_raw + O::IB);
     // the window evaluators' rows (ew rows 0..NWARP-1) are idle, and void, while the chain runs sequentially:
     double *psum = smem_raw + O::EW;                         // 3 x 128 partial sums of the quadratic forms,
-    int *kob = reinterpret_cast<int *>(psum + 3 * SEQ_KMAX); // slots of the staged data's own components (SEQ_BATCH ints),
-    double *rkb = psum + 3 * SEQ_KMAX + SEQ_BATCH / 2;       // 2 x 2: the UU owner's count-table chunk (cp.async target)
+    int *kob = reinterpret_cast<int *>(psum + 3 * SEQ_KMAX); // slots of the staged data's own components (SEQ_BATCH ints)
     double *qv = smem_raw + O::EW + NWARP * Ly::WS;          // f_step's row: the quadratic forms of this datum
     double *vpb = smem_raw + O::DV;                          // dv, vv, nt are contiguous: 2 x 3 x DP partial products
-    double *ntb = qv + SEQ_KMAX;                             // 2 x 8 count-table entries (cp.async targets, 16-B aligned)
-    double *gdb = ntb + 16;                                  // (gam, den) of the two rank-one updates
+    double *gdb = psum + 3 * SEQ_KMAX + SEQ_BATCH / 2;       // (gam, den, -+1/kappa') of the two rank-one updates (6, pad 8)
+    // count-table rows (cp.async targets, 16-B aligned): [0, 8) / [8, 16) of the component the datum may leave, by the
+    // parity of the datum (a request that is never used must not land on the next datum's), [16, 24) of the one it joins
+    double *ntb = gdb + 8;
     const double *fmtab = smem_raw + O::FM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = tid & (SEQ_KMAX - 1);
+    // warp -> (part, group of 32 components): see seq_part_of_warp; this thread's component is k
+    const int grp = seq_group_of_warp(warp);
+    const int k = grp * 32 + lane;
     double *col = rec + k;
     const double *mu = col + Ly::MU * ST;
     double *sc = col + Ly::SC * ST;
@@ -314,6 +345,14 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
             int k_new = -1;
             if (!rare) {
                 const double *x = xb + jj * DP;
+                if constexpr (PART == 0) {
+                    // the count-table rows the component would need if the datum leaves it: requested now, used (if at
+                    // all) at the end of the move
+                    if (k == k_old) {
+                        const long long n_cur = (long long)sc[F_N * ST];
+                        if (n_cur >= 2) seq_fetch_rows(p.ntab, n_cur, ntb + (jj & 1) * 8, true);
+                    }
+                }
                 // ---- phase A: the quadratic forms, four threads per component ----
                 double pq = 0.0;
                 if (k < K) pq = seq_quad_part<DP, PART, ST>(B, col, mu, x);
@@ -341,7 +380,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                         const double t = __shfl_up_sync(0xffffffffu, incl, o);
                         if (lane >= o) incl += t;
                     }
-                    if (lane == 31) sh.wtot[warp] = incl;
+                    if (lane == 31) sh.wtot[grp] = incl;
                     SEQ_T(3);   // finish + scan
                     bar_sync_front();                                                  // #2 (warps 0..3)
                     SEQ_T(4);   // wait at #2
@@ -349,14 +388,14 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                     const double p1 = w0, p2 = w0 + w1, p3 = p2 + w2, tot = p3 + w3;
                     const double t0 = ub[jj] * tot;
                     const int hitw = (p1 > t0) ? 0 : (p2 > t0) ? 1 : (p3 > t0) ? 2 : (tot > t0) ? 3 : 4;
-                    if (warp == hitw) {
-                        const double pre = (warp == 0) ? 0.0 : (warp == 1) ? p1 : (warp == 2) ? p2 : p3;
+                    if (grp == hitw) {
+                        const double pre = (grp == 0) ? 0.0 : (grp == 1) ? p1 : (grp == 2) ? p2 : p3;
                         double excl = __shfl_up_sync(0xffffffffu, incl, 1);
                         if (lane == 0) excl = 0.0;
                         const double upper = pre + incl, lower = pre + excl;
                         const unsigned who = __ballot_sync(0xffffffffu, upper > t0);
                         if (who != 0u && lane == __ffs(who) - 1) {
-                            sh.k_new = tid;
+                            sh.k_new = k;
                             sh.last_mg = (double)__fdividef((float)fmin(t0 - lower, upper - t0), (float)tot);
                         }
                     }
@@ -408,36 +447,26 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
             if (mine) {
                 const double *x = xb + jj * DP;
                 if constexpr (PART == 0) {
-                    // count-table rows n2 - 1 and n2 straight into shared memory (cp.async: an L2 round trip that costs
-                    // no register and is first waited for after the matrix update)
-                    const long long n_cur = (long long)sc[F_N * ST];
-                    const double *r0 = p.ntab + (size_t)(n_cur + (which ? 0 : -2)) * NT_W;
-                    const uint32_t dst = smem_u32(ntb + which * 8);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(r0) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(r0 + NT_W) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 32), "l"(r0 + NT_W + 2) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 48), "l"(r0 + NT_W + 4) : "memory");
+                    // count-table rows n2 - 1 and n2 of the component the datum joins, straight into shared memory
+                    // (cp.async: an L2 round trip that costs no register; first needed for the scalars at the very end of
+                    // the move).  Those of the component it leaves were requested at the head of the step.
+                    if (which) seq_fetch_rows(p.ntab, (long long)sc[F_N * ST], ntb + 16);
+                }
+                if constexpr (PART == 1) {
+                    // the scalars of the two rank-one updates, by the other triangle's owner (it has no rows to fetch):
                     // beta = kappa / (kappa -+ 1): BETA(n) for the removal, G(n) for the addition
                     const double beta = which ? sc[F_G * ST] : sc[F_BETA * ST];
                     const double sq = qv[k];
                     const double den = which ? 1.0 + beta * sq : 1.0 - beta * sq;
-                    // 1 / den without a division (its slow path is a call, and a call with the B block live would put
-                    // part of the block on the stack): single-precision seed, three Newton steps
-                    float rf;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)den));
-                    double rd = (double)rf;
-                    rd = fma(rd, fma(-den, rd, 1.0), rd);
-                    rd = fma(rd, fma(-den, rd, 1.0), rd);
-                    rd = fma(rd, fma(-den, rd, 1.0), rd);
-                    gdb[which * 2] = which ? -(beta * rd) : beta * rd;
-                    gdb[which * 2 + 1] = den;
-                }
-                if constexpr (PART == 1) {
-                    // 1 / kappa(n2) for the means this thread owns: its own copy of that count-table chunk
-                    const long long n_cur = (long long)sc[F_N * ST];
-                    const double *r1 = p.ntab + (size_t)(n_cur + (which ? 1 : -1)) * NT_W;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(rkb + which * 2)), "l"(r1 + NT_RK)
-                                 : "memory");
+                    const double n2 = sc[F_N * ST] + (which ? 1.0 : -1.0);
+                    // reciprocals without a division (its slow path is a call, and a call with the B block live would
+                    // put part of the block on the stack; nor an L2 trip for 1 / kappa): single-precision seed, three
+                    // Newton steps
+                    const double rd = seq_recip(den);
+                    const double rk = seq_recip(p.k0 + n2);
+                    gdb[which * 3] = which ? -(beta * rd) : beta * rd;
+                    gdb[which * 3 + 1] = den;
+                    gdb[which * 3 + 2] = which ? -rk : rk;   // m' = m -+ d / kappa(n2), d = m - x
                 }
                 seq_partial_v<DP, PART, ST>(B, col, mu, x, vp);
             }
@@ -455,14 +484,11 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
             bar_sync_all();                                                            // #4
             SEQ_T(8);   // wait at #4
             if (mine) {
-                seq_rank_one<DP, PART, ST>(B, col, vp, gdb[which * 2]);
-                if constexpr (G::TRI) asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's own copies
-                const double *nt = ntb + which * 8;   // r0: CN, G | r1: CN, G, H, BETA, RK
+                seq_rank_one<DP, PART, ST>(B, col, vp, gdb[which * 3]);
                 if constexpr (G::TRI) {
-                    // m' = m -+ d / kappa(n2), d = m - x  (this thread is the only writer of these means)
+                    // this thread is the only writer of these means
                     const double *x = xb + jj * DP;
-                    const double rk = (PART == 0) ? nt[6] : rkb[which * 2];
-                    const double rk2 = which ? -rk : rk;
+                    const double rk2 = gdb[which * 3 + 2];
 #pragma unroll
                     for (int a = 0; a < G::TN; ++a) {
                         double *pm = col + (Ly::MU + G::O + a) * ST;
@@ -472,11 +498,13 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                 }
                 if constexpr (PART == 0) {
                     const double n2 = sc[F_N * ST] + (which ? 1.0 : -1.0);
-                    const double lds = sc[F_LDS * ST] + fm::f_log(gdb[which * 2 + 1], fmtab);   // matrix determinant lemma
+                    const double lds = sc[F_LDS * ST] + fm::f_log(gdb[which * 3 + 1], fmtab);   // matrix determinant lemma
                     const double cnt = sc[F_CNT * ST] + 1.0;
                     sc[F_N * ST] = n2;
                     sc[F_LDS * ST] = lds;
                     sc[F_CNT * ST] = cnt;
+                    asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's own copies
+                    const double *nt = ntb + (which ? 16 : (jj & 1) * 8);   // r0: CN, G | r1: CN, G, H, BETA, RK
                     sc[F_CW * ST] = nt[2] - 0.5 * lds;
                     sc[F_G * ST] = nt[3];
                     sc[F_H * ST] = nt[4];
@@ -524,9 +552,9 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     return seq;
 }
 
-// dispatch by warp: part = warp / 4
+// dispatch by warp (seq_part_of_warp)
 template <int DP> __device__ __forceinline__ int f_seq_run(const Params &p, const FSmem<DP> &s, int seq) {
-    switch (threadIdx.x >> 7) {
+    switch (seq_part_of_warp(threadIdx.x >> 5)) {
         case 0: return f_seq_part<DP, 0>(p, s, seq);
         case 1: return f_seq_part<DP, 1>(p, s, seq);
         case 2: return f_seq_part<DP, 2>(p, s, seq);

@@ -10,7 +10,9 @@ nvcc $F -c pybgmm_b200/build/inst/inst_full_16.cu -o $B/full16.o &
 nvcc $F -c pybgmm_b200/build/inst/inst_diag_16.cu -o $B/diag16.o &
 nvcc $F -c pybgmm_b200/build/inst/inst_full_2.cu -o $B/full2.o &
 nvcc $F -c pybgmm_b200/build/inst/inst_diag_2.cu -o $B/diag2.o &
+nvcc $F -c pybgmm_b200/build/inst/inst_fixed_16.cu -o $B/fixed16.o &
+nvcc $F -c pybgmm_b200/build/inst/inst_fixed_2.cu -o $B/fixed2.o &
 g++ -O2 -fPIC -c pybgmm_b200/csrc/mt19937.cc -o $B/mt.o &
 wait
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $B/lib.tmp $B/engine.o $B/full16.o $B/diag16.o $B/full2.o $B/diag2.o $B/mt.o && mv $B/lib.tmp pybgmm_b200/lib/libbgmm_b200_prof.so
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $B/lib.tmp $B/engine.o $B/full16.o $B/diag16.o $B/full2.o $B/diag2.o $B/fixed16.o $B/fixed2.o $B/mt.o && mv $B/lib.tmp pybgmm_b200/lib/libbgmm_b200_prof.so
 echo built pybgmm_b200/lib/libbgmm_b200_prof.so
