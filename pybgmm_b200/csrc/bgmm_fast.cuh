@@ -1078,8 +1078,13 @@ __device__ __noinline__ void f_move_phase(const Params &p, const FSmem<DP> &s, i
             sh.dlog_b[v & (DLOG - 1)] = k_new;
             if (died || expl) sh.dall_ver = v;
         }
-    } else if (p.writer && warp >= 8) {
-        // CTA 0: the bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition)
+    }
+    __syncthreads();
+    if (p.writer && warp >= 8) {
+        // The writer CTA: the bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition), issued
+        // behind the move's barrier: a CTA barrier waits for the warp's outstanding global reductions (an L2 round trip
+        // behind ~150 of them), and from here the next barrier is an evaluation away.  Reductions of consecutive moves to
+        // one address stay ordered by the barriers between them; every reader of the statistics sits behind one.
         if (warp < 12) {
             if (remove_now) f_stats_axpy<DP>(p, s.rc, k_old, xs, -1, 0, tid - 256, 128);
         } else {
@@ -1087,7 +1092,6 @@ __device__ __noinline__ void f_move_phase(const Params &p, const FSmem<DP> &s, i
             if (tid == 384) __stcg(p.z_out + s.ib[jj], s.uid_of_slot[k_new]);  // replicas keep reading the input labels
         }
     }
-    __syncthreads();
     F_PROF(PH_UPDATE);
     F_COUNT(PH_MOVES);
     const bool ra = (sh.refresh_a == seq), rb = (sh.refresh_b == seq);

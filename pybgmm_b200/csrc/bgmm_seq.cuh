@@ -470,16 +470,6 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                 }
                 seq_partial_v<DP, PART, ST>(B, col, mu, x, vp);
             }
-            if (p.writer && warp >= 8) {
-                // the bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition)
-                const double *xg = s.xb + jj * DP;
-                if (warp < 12) {
-                    f_stats_axpy_inl<DP>(p, s.rc, k_old, xg, -1, 0, tid - 256, 128);
-                } else {
-                    f_stats_axpy_inl<DP>(p, s.rc, k_new, xg, +1, 0, tid - 384, 128);
-                    if (tid == 384) __stcg(p.z_out + ib[jj], s.uid_of_slot[k_new]);
-                }
-            }
             SEQ_T(7);   // decision + first half of the move
             bar_sync_all();                                                            // #4
             SEQ_T(8);   // wait at #4
@@ -517,6 +507,20 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
             SEQ_T(9);   // second half of the move
             bar_sync_all();                                                            // #5
             SEQ_T(10);  // wait at #5
+            if (p.writer && warp >= 8) {
+                // The bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition), issued AFTER the
+                // move's last barrier: a CTA barrier waits for the warp's outstanding global reductions (an L2 round trip
+                // behind ~150 of them: ~2 k cycles when they sat in front of barrier #4), and from here the next barrier is
+                // a whole evaluation away.  Reductions of consecutive moves to one address stay ordered: five barriers
+                // lie between them.
+                const double *xg = s.xb + jj * DP;
+                if (warp < 12) {
+                    f_stats_axpy_inl<DP>(p, s.rc, k_old, xg, -1, 0, tid - 256, 128);
+                } else {
+                    f_stats_axpy_inl<DP>(p, s.rc, k_new, xg, +1, 0, tid - 384, 128);
+                    if (tid == 384) __stcg(p.z_out + ib[jj], s.uid_of_slot[k_new]);
+                }
+            }
             F_PROF(PH_UPDATE);
             F_COUNT(PH_MOVES);
             const bool ra = (sh.refresh_a == seq), rb = (sh.refresh_b == seq);
