@@ -270,6 +270,19 @@ __device__ __forceinline__ void seq_fetch_rows(const double *ntab, long long n_c
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 48), "l"(r0 + NT_W + 4) : "memory");
 }
 
+// TMA bulk reduction: global[0..n) += shared[0..n) (doubles), element-wise IEEE adds at the L2, asynchronous
+__device__ __forceinline__ void seq_bulk_add(double *gdst, const double *ssrc, int n) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_u32(ssrc)), "r"(n * 8)
+                 : "memory");
+}
+// all bulk groups of this thread have completed (their global writes are performed); then make this CTA's shared
+// memory writes visible to the TMA for the next group
+__device__ __forceinline__ void seq_bulk_wait() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Sequential batches with the B blocks in registers, for the warps of part PART.  Every warp of the CTA calls its own
 // instantiation; all take the same (CTA-uniform) decisions and meet at the same barriers.  Returns when the sweep is
@@ -298,6 +311,11 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     // count-table rows (cp.async targets, 16-B aligned): [0, 8) / [8, 16) of the component the datum may leave, by the
     // parity of the datum (a request that is never used must not land on the next datum's), [16, 24) of the one it joins
     double *ntb = gdb + 8;
+    // the writer CTA's statistics deltas of a move: [parity of the move][leaves / joins][S packed (PP), num (DP)]
+    constexpr bool BULK = (Ly::PP % 2 == 0) && (DP % 2 == 0);   // TMA bulk operands are 16-byte granules
+    constexpr int NSP = Ly::PP + DP;
+    double *dbuf = ntb + 24;
+    int mvpar = 0;
     const double *fmtab = smem_raw + O::FM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warp -> (part, group of 32 components): see seq_part_of_warp; this thread's component is k
@@ -420,8 +438,10 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                 }
             }
             if (rare) {
-                // registers back to the shared-memory records, the general step (bgmm_fast.cuh), registers again
+                // registers back to the shared-memory records, the general step (bgmm_fast.cuh), registers again; the
+                // general step reads and writes the statistics itself: outstanding bulk reductions complete first
                 seq_store_block<DP, PART, ST>(col, B);
+                if (BULK && p.writer && tid == 384) seq_bulk_wait();
                 bar_sync_all();
                 f_step<DP>(p, s, jj, seq);
                 bar_sync_all();
@@ -470,6 +490,23 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                 }
                 seq_partial_v<DP, PART, ST>(B, col, mu, x, vp);
             }
+            if constexpr (BULK) {
+                if (p.writer && warp >= 8) {
+                    // the bit-exact statistics change as two delta vectors in shared memory (warps 8..11: the component
+                    // the datum leaves, 12..15: the one it joins): -+ fl(x_a x_b) and -+ x_a, the reference's operands
+                    // (gaussian_components.py:165-166, :184-185); added to global memory by the TMA below
+                    const double *xg = xb + jj * DP;
+                    const int side = warp >= 12 ? 1 : 0;
+                    double *db = dbuf + (mvpar * 2 + side) * NSP;
+                    const unsigned short *rcs = s.rc;
+                    for (int e = tid - (side ? 384 : 256); e < NSP; e += 128) {
+                        double v;
+                        if (e < Ly::PP) { const int a = rcs[e] >> 8, b = rcs[e] & 0xff; v = __dmul_rn(xg[a], xg[b]); }
+                        else v = xg[e - Ly::PP];
+                        db[e] = side ? v : -v;
+                    }
+                }
+            }
             SEQ_T(7);   // decision + first half of the move
             bar_sync_all();                                                            // #4
             SEQ_T(8);   // wait at #4
@@ -507,12 +544,27 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
             SEQ_T(9);   // second half of the move
             bar_sync_all();                                                            // #5
             SEQ_T(10);  // wait at #5
-            if (p.writer && warp >= 8) {
-                // The bit-exact statistics and the label (warps 8..11 the removal, 12..15 the addition), issued AFTER the
-                // move's last barrier: a CTA barrier waits for the warp's outstanding global reductions (an L2 round trip
-                // behind ~150 of them: ~2 k cycles when they sat in front of barrier #4), and from here the next barrier is
-                // a whole evaluation away.  Reductions of consecutive moves to one address stay ordered: five barriers
-                // lie between them.
+            if constexpr (BULK) {
+                // One thread hands the four delta vectors to the TMA: element-wise IEEE round-to-nearest adds performed at
+                // the L2 (cp.reduce.async.bulk .add.f64, SASS UBLKRED.ADD.F64.RN) -- the same bits as the reference's
+                // `+=` / `-=`, and no warp waits for them: per-thread global reductions (RED.ADD.F64) in front of a CTA
+                // barrier cost ~2 k cycles per move here, because the barrier waits for the warp's outstanding reductions.
+                // Moves that touch one component stay ordered: the previous move's group has completed before this one is
+                // issued (wait_group 0; it is a whole step old), and the parity buffers keep a group's source intact.
+                if (p.writer && tid == 384) {
+                    seq_bulk_wait();
+                    const double *db = dbuf + mvpar * 2 * NSP;
+                    seq_bulk_add(p.S + (size_t)k_old * Ly::PP, db, Ly::PP);
+                    seq_bulk_add(p.num + (size_t)k_old * DP, db + Ly::PP, DP);
+                    seq_bulk_add(p.S + (size_t)k_new * Ly::PP, db + NSP, Ly::PP);
+                    seq_bulk_add(p.num + (size_t)k_new * DP, db + NSP + Ly::PP, DP);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    __stcg(p.z_out + ib[jj], s.uid_of_slot[k_new]);   // the label (replicas keep reading the input copy)
+                }
+                mvpar ^= 1;
+            } else if (p.writer && warp >= 8) {
+                // D <= 2 (the statistics of a component are not a whole number of 16-byte granules): per-thread global
+                // reductions (warps 8..11 the removal, 12..15 the addition), issued behind the move's last barrier
                 const double *xg = s.xb + jj * DP;
                 if (warp < 12) {
                     f_stats_axpy_inl<DP>(p, s.rc, k_old, xg, -1, 0, tid - 256, 128);
@@ -527,6 +579,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
             if (ra || rb) {
                 // drift control: the record(s) again from the bit-exact statistics (needs the shared-memory records)
                 seq_store_block<DP, PART, ST>(col, B);
+                if (BULK && p.writer && tid == 384) seq_bulk_wait();
                 bar_sync_all();
                 const double n_a = ra ? rec[(Ly::SC + F_N) * ST + k_old] : 0.0;
                 const double n_b = rec[(Ly::SC + F_N) * ST + k_new];
@@ -552,6 +605,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     // registers back to the shared-memory records; the window evaluators' cached rows are void
     seq_store_block<DP, PART, ST>(col, B);
     if (tid == 0) { sh.ver += 1; sh.dall_ver = sh.ver; }
+    if (BULK && p.writer && tid == 384) seq_bulk_wait();   // the deltas' buffers are the window evaluators' rows
     bar_sync_all();
     return seq;
 }
