@@ -1,0 +1,460 @@
+// bgmm_big.cuh -- the cluster-resident sweep engine for full covariance (NIW) components with padded D = 32 / 64.
+//
+// Semantics: the per-datum loop of CRPMM / PCRPMM.collapsed_gibbs_sampler (igmm/crpmm.py:57-88, igmm/pcrpmm.py:93-131),
+// strictly sequential over the scan order -- the common case of a step (the datum stays, or moves between two live
+// components); everything else ends the launch and is resolved by the generic engine (bgmm_sweep.cuh) on the host's
+// next turn.
+//
+// At D = 64 one component's evaluation record (B = S_N^-1 packed, the mean, the scalars) is 17 KB and K = 100 of them are
+// 1.7 MB: no SM holds them.  A thread-block CLUSTER does: 16 CTAs (4 at D = 32) on 16 SMs of one GPC, component k owned
+// by CTA k mod C.  One step of the chain:
+//   1. every CTA evaluates the quadratic forms and weights of the components it owns (a group of D/2 lanes per
+//      component, rows r and D-1-r of the triangle per lane: D + 1 elements each, stored lane-interleaved so that the
+//      loads are conflict-free), and stores exp(weight - reference) straight into CTA 0's shared memory
+//      (st.shared::cluster through DSMEM);
+//   2. cluster barrier (hardware: barrier.cluster arrive.release / wait.acquire);
+//   3. CTA 0 scans the K + 1 choices and draws (utils.py:7-20), and writes the result into every CTA's shared memory;
+//   4. cluster barrier;
+//   5. the owner(s) of the two touched components apply the rank-one update of B (Sherman-Morrison), the mean, the
+//      scalars, and send the bit-exact statistics change to global memory with TMA bulk reductions.
+// Two cluster barriers per datum, no global memory on the critical path.  Records are rebuilt from the bit-exact
+// statistics at every launch (k_big_prep), and a launch covers at most BIG_SPAN data, which bounds the drift of the
+// incrementally updated records like REFRESH_EVERY does in bgmm_fast.cuh.
+#pragma once
+#include "bgmm_fast.cuh"
+
+namespace bgmm {
+namespace big {
+
+using fast::F_N; using fast::F_LDS; using fast::F_CNT; using fast::F_CW; using fast::F_G; using fast::F_H;
+using fast::F_BETA; using fast::F_CWO; using fast::NSC;
+using fast::NT_CN; using fast::NT_G; using fast::NT_H; using fast::NT_BETA; using fast::NT_W;
+
+constexpr int TB = 512;              // threads per CTA
+constexpr int SB = 16;               // data staged per batch
+constexpr int KCH = 128;             // choices (K + 1) held by warps 0..3 of CTA 0
+constexpr int E_RARE = 2;            // internal: the datum at Ctl::pos needs the general step
+constexpr long long BIG_SPAN = 1 << 16;   // data per launch (records are rebuilt from the statistics between launches)
+
+template <int DP> struct BL {
+    static constexpr int PP = DP * (DP + 1) / 2;
+    static constexpr int NL = DP / 2;          // lanes per component in the evaluation
+    static constexpr int EPL = DP + 1;         // matrix elements per lane: rows r and DP - 1 - r
+    static constexpr int MU = PP, SC = PP + DP, R = PP + DP + NSC;
+    static constexpr int C = (DP == 64) ? 16 : 4;        // CTAs per cluster
+    static constexpr int LMAX = KCH / C;                 // components per CTA
+    static constexpr int SLOTS = TB / NL;                // groups of NL lanes per CTA
+    static constexpr int SPC = SLOTS / LMAX;             // lane groups per component (they split the elements of a lane)
+    static constexpr int SEGS = TB / DP;                 // v = B d: threads per row
+    static constexpr int CPS = DP / SEGS;                //          columns per thread
+    static_assert(SPC >= 1 && SLOTS % LMAX == 0, "lane groups must tile the components");
+    static_assert(SEGS <= 32 && DP % SEGS == 0, "a row's threads sit in one warp");
+};
+
+// storage index of element (a, b), a >= b, of the packed triangle: lane-interleaved rows r / DP - 1 - r
+template <int DP> __host__ __device__ __forceinline__ int pidx(int a, int b) {
+    constexpr int NL = BL<DP>::NL;
+    const int lane = a < NL ? a : DP - 1 - a;
+    const int j = a < NL ? b : b + lane + 1;
+    return j * NL + lane;
+}
+
+__device__ __forceinline__ unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(const void *smem_ptr, unsigned rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(smem_ptr)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_remote_f64(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_remote_u32(uint32_t addr, unsigned v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+struct BSh {
+    // result of the draw, written by CTA 0 into every CTA (remote stores), read after the second cluster barrier
+    double res_mg;
+    int res_k, res_rare;
+    // CTA-local
+    double wtot[4];
+    double gam, den, rk;
+    long long moves, evals, steps;
+    unsigned long long margin_bits;
+    int K, stop;
+};
+
+template <int DP> struct BSmem {
+    double *rec;      // LMAX * R: the records this CTA owns, local component l = k / C
+    double *dsh;      // LMAX * DP: d = m - x of the datum for every owned component
+    double *qpart;    // SLOTS partial quadratic forms
+    double *qloc;     // LMAX
+    double *ebuf;     // KCH: exp(weight - reference) of every choice (used in CTA 0)
+    double *vbuf;     // DP: v = B d of the component being updated
+    double *dlt;      // 2 x (PP + DP): statistics deltas for the TMA (parity buffers)
+    double *xb, *ub, *lpb;
+    long long *ib;
+    int *uidb, *kob;
+    double *fm;
+    int *slot_of_uid, *uid_of_slot;
+    unsigned short *rc;   // PP: (a << 8) | b of row-major packed element e (the statistics' order)
+    BSh *sh;
+};
+
+template <int DP> __host__ __device__ inline size_t big_smem_bytes(int K_max) {
+    using L = BL<DP>;
+    size_t d = (size_t)L::LMAX * L::R + (size_t)L::LMAX * DP + L::SLOTS + L::LMAX + KCH + DP + 2 * (size_t)(L::PP + DP) +
+               (size_t)SB * DP + 2 * SB + SB + SB + fm::TAB_LEN + 8;
+    size_t b = d * sizeof(double) + 2 * (size_t)K_max * sizeof(int) + (((size_t)L::PP + 7) & ~(size_t)7) * sizeof(unsigned short) +
+               ((sizeof(BSh) + 15) & ~(size_t)15) + 64;
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int DP> __device__ inline BSmem<DP> big_carve(double *base, int K_max) {
+    using L = BL<DP>;
+    BSmem<DP> s;
+    double *q = base;
+    s.rec = q; q += (size_t)L::LMAX * L::R;
+    s.dsh = q; q += (size_t)L::LMAX * DP;
+    s.qpart = q; q += L::SLOTS;
+    s.qloc = q; q += L::LMAX;
+    s.ebuf = q; q += KCH;
+    s.vbuf = q; q += DP;
+    s.dlt = q; q += 2 * (L::PP + DP);
+    s.xb = q; q += SB * DP;
+    s.ub = q; q += SB;
+    s.lpb = q; q += SB;
+    s.ib = (long long *)q; q += SB;
+    s.uidb = (int *)q; q += SB / 2;
+    s.kob = (int *)q; q += SB / 2;
+    s.fm = q; q += fm::TAB_LEN;
+    q = (double *)(((uintptr_t)q + 15) & ~(uintptr_t)15);
+    s.sh = (BSh *)q;
+    unsigned short *r = (unsigned short *)((char *)q + ((sizeof(BSh) + 15) & ~(size_t)15));
+    s.rc = r; r += (L::PP + 7) & ~7;
+    int *t = (int *)r;
+    s.slot_of_uid = t; t += K_max;
+    s.uid_of_slot = t; t += K_max;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// records of all live components in this engine's layout, from the bit-exact statistics: one warp per component
+// (fast::f_exact_record_warp: Cholesky of S_N, inverse, scalars from the count table), then the triangle permuted into
+// the lane-interleaved order.  Dynamic shared memory: PP + DP * DP + DP doubles + PP shorts.
+// ---------------------------------------------------------------------------------------------
+template <int DP> __global__ void k_big_prep(const Params p, int K, double *__restrict__ rec_out, int *err) {
+    using L = BL<DP>;
+    extern __shared__ __align__(16) double sm[];
+    double *A = sm, *W = A + L::PP, *mm = W + DP * DP, *tmp = mm + DP;
+    unsigned short *rc = (unsigned short *)(tmp + L::R);
+    const int k = blockIdx.x, lane = threadIdx.x;
+    for (int e = lane; e < L::PP; e += 32) {
+        int a, b;
+        decode_row_idx(e, a, b);
+        rc[e] = (unsigned short)((a << 8) | b);
+    }
+    __syncwarp();
+    if (k >= K) return;
+    const bool ok = fast::f_exact_record_warp<DP>(p, 0, p.num + (size_t)k * DP, p.S + (size_t)k * L::PP, (double)p.counts[k],
+                                                  nullptr, rc, A, W, mm, tmp, 1);
+    if (!ok) { if (lane == 0) *err = -4; return; }
+    double *out = rec_out + (size_t)k * L::R;
+    for (int e = lane; e < L::PP; e += 32) out[pidx<DP>(rc[e] >> 8, rc[e] & 0xff)] = tmp[e];
+    for (int e = L::PP + lane; e < L::R; e += 32) out[e] = tmp[e];
+}
+
+// element (hi, lo) of the symmetric matrix for any pair of indices
+template <int DP> __device__ __forceinline__ double bsym(const double *__restrict__ B, int a, int b) {
+    return a >= b ? B[pidx<DP>(a, b)] : B[pidx<DP>(b, a)];
+}
+
+// ---------------------------------------------------------------------------------------------
+// the sweep kernel: one cluster per chain
+// ---------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const double *__restrict__ rec_in, long long pos_limit) {
+    using L = BL<DP>;
+    constexpr int C = L::C, NL = L::NL, R = L::R;
+    extern __shared__ __align__(16) double smem_raw[];
+    __shared__ Params p_sh;
+    __shared__ BSmem<DP> s_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { p_sh = p_in; s_sh = big_carve<DP>(smem_raw, p_in.K_max); }
+    __syncthreads();
+    const Params &p = p_sh;
+    const BSmem<DP> &s = s_sh;
+    BSh &sh = *s.sh;
+    Ctl *ctl = p.ctl;
+    const int c = (int)cluster_rank();
+
+    // ---- prologue ----
+    const int K = __ldcg(&ctl->K);
+    const int Lc = (K > c) ? (K - c + C - 1) / C : 0;     // components this CTA owns: k = l * C + c
+    if (tid == 0) {
+        sh.K = K; sh.stop = 0; sh.moves = sh.evals = sh.steps = 0;
+        const double one = 1.0;
+        sh.margin_bits = (unsigned long long)__double_as_longlong(one);
+        sh.res_k = 0; sh.res_rare = 0; sh.res_mg = 1.0;
+    }
+    for (int l = 0; l < Lc; ++l) {
+        const double *src = rec_in + (size_t)(l * C + c) * R;
+        for (int e = tid; e < R; e += TB) s.rec[(size_t)l * R + e] = __ldcg(src + e);
+    }
+    for (int e = tid; e < fm::TAB_LEN; e += TB) s.fm[e] = __ldg(p.fmtab + e);
+    for (int e = tid; e < L::PP; e += TB) {
+        int a, b;
+        decode_row_idx(e, a, b);
+        s.rc[e] = (unsigned short)((a << 8) | b);
+    }
+    for (int t = tid; t < p.K_max; t += TB) {
+        s.slot_of_uid[t] = __ldcg(p.slot_of_uid + t);
+        s.uid_of_slot[t] = __ldcg(p.uid_of_slot + t);
+    }
+    for (int e = tid; e < KCH; e += TB) s.ebuf[e] = 0.0;
+    __syncthreads();
+    cluster_sync_all();   // every CTA's shared memory is initialised before anyone stores into it remotely
+
+    const uint32_t ebuf0 = map_to_cta(s.ebuf, 0);       // CTA 0's choice buffer
+    int mvpar = 0;
+    long long pos = p.start_pos;
+    bool stop = false;
+    while (pos < pos_limit && !stop) {
+        const int nb = (int)min((long long)SB, pos_limit - pos);
+        __syncthreads();
+        for (int t = tid; t < nb * DP; t += TB) {
+            const int jj = t / DP, a = t % DP;
+            const long long j = pos + jj;
+            const long long i = p.order ? p.order[j] : j;
+            s.xb[jj * DP + a] = p.X[(size_t)i * DP + a];
+            if (a == 0) {
+                s.ib[jj] = i;
+                const int uid = __ldcg(p.z_uid + i);
+                s.uidb[jj] = uid;
+                s.ub[jj] = p.u[j];
+                s.lpb[jj] = p.log_prior[i];
+                s.kob[jj] = uid >= 0 ? s.slot_of_uid[uid] : -1;
+            }
+        }
+        __syncthreads();
+        int done = 0;
+        for (int jj = 0; jj < nb; ++jj) {
+            const int k_old = s.kob[jj];
+            if (k_old < 0) { stop = true; break; }      // an unassigned datum: the general step (same decision in every CTA)
+            const double *x = s.xb + jj * DP;
+            const double wref = p.log_alpha + s.lpb[jj];
+            // ---- 1. quadratic forms and weights of the components this CTA owns ----
+            for (int t = tid; t < Lc * DP; t += TB) {
+                const int l = t / DP, a = t % DP;
+                s.dsh[t] = s.rec[(size_t)l * R + L::MU + a] - x[a];
+            }
+            __syncthreads();
+            {
+                const int slot = tid / NL, ln = tid % NL;
+                const int l = slot / L::SPC, seg = slot % L::SPC;
+                double acc = 0.0;
+                if (l < Lc) {
+                    const double *B = s.rec + (size_t)l * R;
+                    const double *d = s.dsh + l * DP;
+                    // lane ln: row r = ln (columns 0..r at j = 0..r), then row r2 = DP - 1 - ln (columns 0..r2);
+                    // sum_a d_a (sum_{b<a} B_ab d_b + B_aa d_a / 2), the lane's D + 1 elements split over SPC groups
+                    const int r = ln, r2 = DP - 1 - ln;
+                    constexpr int JS = (L::EPL + L::SPC - 1) / L::SPC;
+                    const int j0 = seg * JS, j1 = min(L::EPL, j0 + JS);
+                    double a1 = 0.0, a2 = 0.0;
+                    for (int j = j0; j < j1; ++j) {
+                        const double bv = B[j * NL + ln];
+                        if (j <= r) {
+                            a1 = fma(j == r ? 0.5 * bv : bv, d[j], a1);
+                        } else {
+                            const int b = j - r - 1;
+                            a2 = fma(b == r2 ? 0.5 * bv : bv, d[b], a2);
+                        }
+                    }
+                    acc = d[r] * a1 + d[r2] * a2;
+                }
+#pragma unroll
+                for (int o = NL / 2; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (ln == 0) s.qpart[slot] = acc;
+            }
+            __syncthreads();
+            if (tid < Lc) {
+                const int l = tid, k = l * C + c;
+                double qs = 0.0;
+#pragma unroll
+                for (int g = 0; g < L::SPC; ++g) qs += s.qpart[l * L::SPC + g];
+                const double q = 2.0 * qs;
+                const double *sc = s.rec + (size_t)l * R + L::SC;
+                const int own = (k == k_old) ? 1 : 0;
+                double e = fast::f_finish_weight<1>(sc, q, own, wref, s.fm);
+                if (own && sc[F_N] == 1.0) e = NAN;   // the datum is its component's last member: the general step
+                s.qloc[l] = q;
+                st_remote_f64(ebuf0 + (uint32_t)k * 8u, e);
+            }
+            cluster_sync_all();                                                       // A: all weights are in CTA 0
+            // ---- 3. CTA 0 draws (crpmm.py:75-78, utils.py:7-20) ----
+            if (c == 0 && warp < 4) {
+                const int kk = tid;
+                double e = (kk < K) ? s.ebuf[kk] : (kk == K ? 1.0 : 0.0);
+                double incl = e;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane == 31) sh.wtot[warp] = incl;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const double w0 = sh.wtot[0], w1 = sh.wtot[1], w2 = sh.wtot[2], w3 = sh.wtot[3];
+                const double p1 = w0, p2 = w0 + w1, p3 = p2 + w2, tot = p3 + w3;
+                const double t0 = s.ub[jj] * tot;
+                const int hitw = (p1 > t0) ? 0 : (p2 > t0) ? 1 : (p3 > t0) ? 2 : (tot > t0) ? 3 : 4;
+                int k_new = -1;
+                double mg = 0.0;
+                bool have = false;
+                if (warp == hitw) {
+                    const double pre = (warp == 0) ? 0.0 : (warp == 1) ? p1 : (warp == 2) ? p2 : p3;
+                    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                    if (lane == 0) excl = 0.0;
+                    const double upper = pre + incl, lower = pre + excl;
+                    const unsigned who = __ballot_sync(0xffffffffu, upper > t0);
+                    if (who != 0u && lane == __ffs(who) - 1) {
+                        k_new = kk;
+                        mg = (double)__fdividef((float)fmin(t0 - lower, upper - t0), (float)tot);
+                        have = true;
+                    }
+                }
+                if (tid == 0 && hitw == 4) { k_new = K; mg = 0.0; have = true; }   // utils.py:20 fallback: the last index
+                if (have) {
+                    // anything but a stay or a plain move between two live components ends the launch: a birth, a draw
+                    // inside the margin guard, an untrusted closed form / a component that would die (NaN), overflow
+                    const int rare = (!(tot > 0.0) || !(tot < INFINITY) || k_new >= K || mg < p.guard) ? 1 : 0;
+                    for (int t = 0; t < C; ++t) {
+                        st_remote_f64(map_to_cta(&sh.res_mg, t), mg);
+                        st_remote_u32(map_to_cta(&sh.res_k, t), (unsigned)k_new);
+                        st_remote_u32(map_to_cta(&sh.res_rare, t), (unsigned)rare);
+                    }
+                }
+            }
+            cluster_sync_all();                                                       // B: the draw is in every CTA
+            const int k_new = sh.res_k;
+            if (sh.res_rare) { stop = true; break; }
+            if (tid == 0 && c == 0) {
+                sh.evals += K;
+                sh.steps += 1;
+                const unsigned long long mb = (unsigned long long)__double_as_longlong(sh.res_mg);
+                if (mb < sh.margin_bits) sh.margin_bits = mb;
+            }
+            done = jj + 1;
+            if (k_new == k_old) continue;   // stay: nothing was touched (crpmm.py:82-85)
+
+            // ---- 5. the datum moves: the owners update their records (add_item / del_item as rank-one changes of S_N) ----
+            for (int side = 0; side < 2; ++side) {
+                const int k = side ? k_new : k_old;
+                if (k % C != c) continue;       // uniform over the CTA
+                const int l = k / C;
+                double *B = s.rec + (size_t)l * R;
+                double *sc = B + L::SC;
+                const double *d = s.dsh + l * DP;   // m - x, still this datum's
+                // v = B d: SEGS threads per row, CPS columns each
+                {
+                    const int a = tid / L::SEGS, sg = tid % L::SEGS;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int t = 0; t < L::CPS; ++t) {
+                        const int b = sg * L::CPS + t;
+                        acc = fma(bsym<DP>(B, a, b), d[b], acc);
+                    }
+#pragma unroll
+                    for (int o = L::SEGS / 2; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (sg == 0) s.vbuf[a] = acc;
+                }
+                // scalars of the update and the count-table rows of the new count (thread 0)
+                double cn0 = 0.0, cn1 = 0.0, g1 = 0.0, h1 = 0.0, b1 = 0.0, n2 = 0.0;
+                if (tid == 0) {
+                    const double n = sc[F_N];
+                    n2 = n + (side ? 1.0 : -1.0);
+                    const double *r0 = p.ntab + (size_t)((long long)n2 - 1) * NT_W;
+                    cn0 = __ldg(r0 + NT_CN); cn1 = __ldg(r0 + NT_W + NT_CN); g1 = __ldg(r0 + NT_W + NT_G);
+                    h1 = __ldg(r0 + NT_W + NT_H); b1 = __ldg(r0 + NT_W + NT_BETA);
+                    const double beta = side ? sc[F_G] : sc[F_BETA];
+                    const double den = side ? 1.0 + beta * s.qloc[l] : 1.0 - beta * s.qloc[l];
+                    sh.gam = side ? -beta / den : beta / den;
+                    sh.den = den;
+                    sh.rk = (side ? -1.0 : 1.0) / (p.k0 + n2);   // m' = m -+ d / kappa(n2), d = m - x
+                }
+                // statistics deltas for the TMA (gaussian_components.py:165-166, :184-185: -+ fl(x_a x_b), -+ x_a)
+                double *db = s.dlt + (size_t)mvpar * (L::PP + DP);
+                if (tid == 32) {   // the previous group that read this buffer has long completed; wait for it anyway
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                }
+                __syncthreads();
+                for (int e = tid; e < L::PP + DP; e += TB) {
+                    double v;
+                    if (e < L::PP) { const int a = s.rc[e] >> 8, b = s.rc[e] & 0xff; v = __dmul_rn(x[a], x[b]); }
+                    else v = x[e - L::PP];
+                    db[e] = side ? v : -v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // each writer, in front of the TMA's read
+                const double gam = sh.gam, rk = sh.rk;
+                // rank-one update of the triangle in its storage order: index = j * NL + lane
+                for (int idx = tid; idx < L::PP; idx += TB) {
+                    const int ln = idx % NL, j = idx / NL;
+                    int a, b;
+                    if (j <= ln) { a = ln; b = j; } else { a = DP - 1 - ln; b = j - ln - 1; }
+                    B[idx] = fma(gam * s.vbuf[a], s.vbuf[b], B[idx]);
+                }
+                __syncthreads();   // every reader of d is done before the mean changes
+                if (tid < DP) B[L::MU + tid] = fma(d[tid], rk, B[L::MU + tid]);
+                if (tid == 0) {
+                    const double lds = sc[F_LDS] + fm::f_log(sh.den, s.fm);   // matrix determinant lemma
+                    sc[F_N] = n2;
+                    sc[F_LDS] = lds;
+                    sc[F_CNT] = sc[F_CNT] + 1.0;
+                    sc[F_CW] = cn1 - 0.5 * lds;
+                    sc[F_G] = g1;
+                    sc[F_H] = h1;
+                    sc[F_BETA] = b1;
+                    sc[F_CWO] = cn0 - 0.5 * lds;
+                }
+                __syncthreads();
+                if (tid == 32) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    fast::seq_bulk_add(p.S + (size_t)k * L::PP, db, L::PP);
+                    fast::seq_bulk_add(p.num + (size_t)k * DP, db + L::PP, DP);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                mvpar ^= 1;
+            }
+            if (c == 0 && tid == 0) {
+                __stcg(p.z_uid + s.ib[jj], s.uid_of_slot[k_new]);   // one writer, no replicas: the labels change in place
+                sh.moves += 1;
+            }
+        }
+        pos += done;
+    }
+
+    // ---- epilogue ----
+    if (tid == 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (int l = tid; l < Lc; l += TB) __stcg(p.counts + (l * C + c), (long long)s.rec[(size_t)l * R + L::SC + F_N]);
+    if (c == 0 && tid == 0) {
+        __stcg(&ctl->pos, pos);
+        __stcg(&ctl->error, stop ? E_RARE : 0);
+        __stcg(&ctl->moves, __ldcg(&ctl->moves) + sh.moves);
+        __stcg(&ctl->evals, __ldcg(&ctl->evals) + sh.evals);
+        __stcg(&ctl->seq_data, __ldcg(&ctl->seq_data) + sh.steps);
+        __stcg(&ctl->fast_steps, __ldcg(&ctl->fast_steps) + sh.steps);
+        atomicMin(&ctl->margin_bits, sh.margin_bits);
+    }
+    cluster_sync_all();   // no CTA exits while another may still store into its shared memory
+}
+
+}  // namespace big
+}  // namespace bgmm

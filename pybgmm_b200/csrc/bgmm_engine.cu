@@ -349,7 +349,7 @@ static void free_all(bgmm_handle *h) {
     cudaFree(h->d_counts); cudaFree(h->d_num); cudaFree(h->d_S); cudaFree(h->d_rec); cudaFree(h->d_wbuf);
     cudaFree(h->d_rec_prior); cudaFree(h->d_ctl); cudaFree(h->d_err); cudaFree(h->d_u); cudaFree(h->d_order);
     cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf);
-    cudaFree(h->d_true); cudaFree(h->d_table); cudaFree(h->d_pv);
+    cudaFree(h->d_true); cudaFree(h->d_table); cudaFree(h->d_pv); cudaFree(h->d_recBig);
     // buffers shared with the chains forked from / with this one: freed with the last of them
     if (h->sb && --h->sb->refs == 0) {
         SharedBufs *b = h->sb;
@@ -557,6 +557,7 @@ static int create_impl(const double *X, int64_t N, int32_t D, int32_t cov_type, 
     h->d_m0 = b->d_m0; h->d_S0 = b->d_S0; h->d_tau = b->d_tau;
     if (b->d_tau) CU(cudaMemcpy(b->d_tau, h->tauv.data(), sizeof(double) * DP, cudaMemcpyHostToDevice));
     if (int rc = h->ops->fast_setup(h)) { free_all(h); delete h; return rc; }
+    if (int rc = h->ops->big_setup(h)) { free_all(h); delete h; return rc; }
     if (int rc = alloc_chain_state(h)) { free_all(h); delete h; return rc; }
 
     // uploads
@@ -622,6 +623,7 @@ int bgmm_fork(bgmm_t *parent, bgmm_t **out) {
     h->dX = b->dX; h->d_log_prior = b->d_log_prior; h->d_lgam = b->d_lgam; h->d_logv = b->d_logv;
     h->d_m0 = b->d_m0; h->d_S0 = b->d_S0; h->d_tau = b->d_tau;
     if (int rc = h->ops->fast_setup(h)) { free_all(h); delete h; return rc; }
+    if (int rc = h->ops->big_setup(h)) { free_all(h); delete h; return rc; }
     if (int rc = alloc_chain_state(h)) { free_all(h); delete h; return rc; }
     // the prior's generic record (bgmm_log_prior's source) is per handle: copy the parent's
     CU(cudaMemcpy(h->d_rec_prior, parent->d_rec_prior, sizeof(double) * h->ops->rec_len, cudaMemcpyDeviceToDevice));
@@ -813,8 +815,52 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
             fast = false;
         }
     }
-    const bool ran_fast = fast || generic_from >= 0;
-    if (!fast) {
+    // engine 0..2 on padded D = 32 / 64, full covariance: the cluster engine (bgmm_big.cuh).  A launch walks the chain until
+    // the sweep ends, BIG_SPAN data are done, or a datum needs the general step (a birth, a death, an explicit removal, a
+    // draw inside the margin guard); that datum is resolved by the generic engine's step, the records are rebuilt from the
+    // bit-exact statistics, and the cluster continues behind it.
+    bool big_done = false;
+    if (!fast && generic_from < 0 && h->big_ok && h->engine < 3 && c.K <= h->Kcap && c.K >= 1) {
+        CU(cudaEventRecord(h->ev2, st));
+        long long pos = 0;
+        bool to_generic = false;
+        while (pos < h->N) {
+            p.start_pos = pos;
+            if (int rc = h->ops->big_prep(h, p, c.K)) return rc;
+            if (int rc = check_dev_err(h, "sweep (record set-up)")) return rc;
+            if (int rc = h->ops->big_sweep(h, p, std::min<long long>(h->N, pos + big::BIG_SPAN))) return rc;
+            CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            pos = c.pos;
+            if (c.error == big::E_RARE) {
+                // the generic engine's (Cholesky) records follow from the statistics; its step resolves the datum
+                c.error = 0;
+                CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
+                if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
+                h->launches += 1;
+                if (int rc = h->ops->resolve_one(h, p, pos)) return rc;
+                CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                pos = c.pos;
+                if (c.error != 0) break;
+                if (c.K > h->Kcap || c.K < 1) { to_generic = true; break; }
+            } else if (c.error != 0) {
+                break;
+            }
+        }
+        CU(cudaEventRecord(h->ev3, st));
+        if (to_generic && pos < h->N) {
+            generic_from = pos;   // more live components than the cluster holds: the generic engine finishes the sweep
+        } else {
+            big_done = true;
+            if (c.error == 0 && c.K > 0) {
+                if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
+                h->launches += 1;
+            }
+        }
+    }
+    const bool ran_fast = fast || generic_from >= 0 || big_done;
+    if (!fast && !big_done) {
         p.start_pos = generic_from < 0 ? 0 : generic_from;
         if (!h->d_wbuf) {   // the generic engine's window scratch, on first use
             cudaError_t e_ = cudaMalloc((void **)&h->d_wbuf, sizeof(double) * (size_t)h->grid * (h->K_max + 1) * T_SWEEP);

@@ -1945,13 +1945,15 @@ __device__ __forceinline__ void fast_sweep_body(const Params &p_in) {
     }
 }
 
-template <int DP> __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in) { fast_sweep_body<DP>(p_in); }
-
-// bgmm_sweep_many: CTA c advances chain c (its Params at pv[c]) on its own -- the sequential engine with the CTA as the
-// chain's only replica; chains beyond the number of resident CTAs simply queue (there is no inter-CTA dependency)
-template <int DP> __global__ void __launch_bounds__(TF, 1) k_fast_sweep_many(const Params *__restrict__ pv) {
+// One entry point for both launch shapes (ONE copy of the device functions: ptxas 12.9 was seen to encode the TMA
+// reduction of bgmm_seq.cuh as an integer add -- UBLKRED.ADD.U64 instead of .ADD.F64.RN -- in the second kernel's clone
+// of the same PTX function; tests/test_abi.py checks the shipped SASS):
+//   pv == nullptr: the cooperative grid advances the one chain of p_in (replicated state machine);
+//   pv != nullptr: bgmm_sweep_many -- CTA c advances chain c (its Params at pv[c]) on its own, the sequential engine with
+//                  the CTA as the chain's only replica; chains beyond the number of resident CTAs simply queue.
+template <int DP> __global__ void __launch_bounds__(TF, 1) k_fast_sweep(const Params p_in, const Params *__restrict__ pv) {
     __shared__ Params p_mine;
-    if (threadIdx.x == 0) p_mine = pv[blockIdx.x];
+    if (threadIdx.x == 0) p_mine = pv ? pv[blockIdx.x] : p_in;
     __syncthreads();
     fast_sweep_body<DP>(p_mine);
 }

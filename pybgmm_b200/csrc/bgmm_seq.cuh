@@ -316,6 +316,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     constexpr int NSP = Ly::PP + DP;
     double *dbuf = ntb + 24;
     int mvpar = 0;
+    const bool bulk = BULK && !(p.tune & 16);   // developer switch: bit 4 = per-thread reductions instead of the TMA
     const double *fmtab = smem_raw + O::FM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warp -> (part, group of 32 components): see seq_part_of_warp; this thread's component is k
@@ -441,7 +442,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                 // registers back to the shared-memory records, the general step (bgmm_fast.cuh), registers again; the
                 // general step reads and writes the statistics itself: outstanding bulk reductions complete first
                 seq_store_block<DP, PART, ST>(col, B);
-                if (BULK && p.writer && tid == 384) seq_bulk_wait();
+                if (bulk && p.writer && tid == 384) seq_bulk_wait();
                 bar_sync_all();
                 f_step<DP>(p, s, jj, seq);
                 bar_sync_all();
@@ -490,7 +491,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                 }
                 seq_partial_v<DP, PART, ST>(B, col, mu, x, vp);
             }
-            if constexpr (BULK) {
+            if (bulk) {
                 if (p.writer && warp >= 8) {
                     // the bit-exact statistics change as two delta vectors in shared memory (warps 8..11: the component
                     // the datum leaves, 12..15: the one it joins): -+ fl(x_a x_b) and -+ x_a, the reference's operands
@@ -505,6 +506,9 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                         else v = xg[e - Ly::PP];
                         db[e] = side ? v : -v;
                     }
+                    // the TMA reads shared memory through the async proxy: every writing thread orders its own generic
+                    // writes in front of it (the issuing thread's fence alone does not cover other threads' writes)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 }
             }
             SEQ_T(7);   // decision + first half of the move
@@ -544,7 +548,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
             SEQ_T(9);   // second half of the move
             bar_sync_all();                                                            // #5
             SEQ_T(10);  // wait at #5
-            if constexpr (BULK) {
+            if (bulk) {
                 // One thread hands the four delta vectors to the TMA: element-wise IEEE round-to-nearest adds performed at
                 // the L2 (cp.reduce.async.bulk .add.f64, SASS UBLKRED.ADD.F64.RN) -- the same bits as the reference's
                 // `+=` / `-=`, and no warp waits for them: per-thread global reductions (RED.ADD.F64) in front of a CTA
@@ -559,6 +563,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                     seq_bulk_add(p.S + (size_t)k_new * Ly::PP, db + NSP, Ly::PP);
                     seq_bulk_add(p.num + (size_t)k_new * DP, db + NSP + Ly::PP, DP);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (p.tune & 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // developer switch: synchronous
                     __stcg(p.z_out + ib[jj], s.uid_of_slot[k_new]);   // the label (replicas keep reading the input copy)
                 }
                 mvpar ^= 1;
@@ -579,7 +584,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
             if (ra || rb) {
                 // drift control: the record(s) again from the bit-exact statistics (needs the shared-memory records)
                 seq_store_block<DP, PART, ST>(col, B);
-                if (BULK && p.writer && tid == 384) seq_bulk_wait();
+                if (bulk && p.writer && tid == 384) seq_bulk_wait();
                 bar_sync_all();
                 const double n_a = ra ? rec[(Ly::SC + F_N) * ST + k_old] : 0.0;
                 const double n_b = rec[(Ly::SC + F_N) * ST + k_new];
@@ -605,7 +610,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     // registers back to the shared-memory records; the window evaluators' cached rows are void
     seq_store_block<DP, PART, ST>(col, B);
     if (tid == 0) { sh.ver += 1; sh.dall_ver = sh.ver; }
-    if (BULK && p.writer && tid == 384) seq_bulk_wait();   // the deltas' buffers are the window evaluators' rows
+    if (bulk && p.writer && tid == 384) seq_bulk_wait();   // the deltas' buffers are the window evaluators' rows
     bar_sync_all();
     return seq;
 }

@@ -71,3 +71,19 @@ def test_oracle_is_not_imported_by_the_product():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
                 assert "liboracle" not in text and "orc_" not in text, os.path.join(dirpath, f)
+
+
+def test_tma_reductions_are_fp64_adds():
+    """The statistics deltas go to global memory as TMA bulk reductions (cp.reduce.async.bulk ... .add.f64).  ptxas 12.9
+    was seen to encode that PTX as an INTEGER add (UBLKRED.G.S.ADD.U64) in one of two kernels that shared the device
+    function; the shipped SASS must hold the fp64 form only."""
+    import shutil
+    import subprocess
+    from pybgmm_b200 import _lib
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    kinds = set(re.findall(r"UBLKRED\S*", out))
+    assert kinds, "no TMA reduction in the library"
+    assert kinds == {"UBLKRED.G.S.ADD.F64.RN"}, kinds
