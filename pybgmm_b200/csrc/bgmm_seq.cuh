@@ -276,6 +276,20 @@ __device__ __forceinline__ void seq_bulk_add(double *gdst, const double *ssrc, i
                  "r"(smem_u32(ssrc)), "r"(n * 8)
                  : "memory");
 }
+// the bulk group committed `m` groups ago (m >= 1: the latest is 1) has completed, i.e. at most m - 1 of the most
+// recent groups are still pending; nothing older than 8 groups is ever left pending
+__device__ __forceinline__ void seq_bulk_wait_older(int m) {
+    switch (m) {
+        case 1: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.bulk.wait_group 5;" ::: "memory"); break;
+        case 7: asm volatile("cp.async.bulk.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group 7;" ::: "memory"); break;
+    }
+}
 // all bulk groups of this thread have completed (their global writes are performed); then make this CTA's shared
 // memory writes visible to the TMA for the next group
 __device__ __forceinline__ void seq_bulk_wait() {
@@ -315,6 +329,10 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     constexpr bool BULK = (Ly::PP % 2 == 0) && (DP % 2 == 0);   // TMA bulk operands are 16-byte granules
     constexpr int NSP = Ly::PP + DP;
     double *dbuf = ntb + 24;
+    // move counter of the last bulk group that touched each component (the issuing thread's bookkeeping)
+    int *lastmv = reinterpret_cast<int *>(dbuf + 4 * NSP);
+    if (tid < SEQ_KMAX) lastmv[tid] = -1000;
+    int mvcount = 0;
     int mvpar = 0;
     const bool bulk = BULK && !(p.tune & 16);   // developer switch: bit 4 = per-thread reductions instead of the TMA
     const double *fmtab = smem_raw + O::FM;
@@ -553,20 +571,28 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                 // the L2 (cp.reduce.async.bulk .add.f64, SASS UBLKRED.ADD.F64.RN) -- the same bits as the reference's
                 // `+=` / `-=`, and no warp waits for them: per-thread global reductions (RED.ADD.F64) in front of a CTA
                 // barrier cost ~2 k cycles per move here, because the barrier waits for the warp's outstanding reductions.
-                // Moves that touch one component stay ordered: the previous move's group has completed before this one is
-                // issued (wait_group 0; it is a whole step old), and the parity buffers keep a group's source intact.
+                // Moves that touch one component stay ordered: the last group that touched either component has completed
+                // before this one is issued (wait_group on its age; it usually is many steps old), and the parity buffers
+                // keep a group's source intact until it has been read.
                 if (p.writer && tid == 384) {
-                    seq_bulk_wait();
+                    // order: the last group that touched either component has completed (it usually is many groups old)
+                    seq_bulk_wait_older(mvcount - max(lastmv[k_old], lastmv[k_new]));
+                    lastmv[k_old] = mvcount;
+                    lastmv[k_new] = mvcount;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     const double *db = dbuf + mvpar * 2 * NSP;
                     seq_bulk_add(p.S + (size_t)k_old * Ly::PP, db, Ly::PP);
                     seq_bulk_add(p.num + (size_t)k_old * DP, db + Ly::PP, DP);
                     seq_bulk_add(p.S + (size_t)k_new * Ly::PP, db + NSP, Ly::PP);
                     seq_bulk_add(p.num + (size_t)k_new * DP, db + NSP + Ly::PP, DP);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    // the other parity's buffers are refilled by the next move: their group's source reads are done
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     if (p.tune & 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // developer switch: synchronous
                     __stcg(p.z_out + ib[jj], s.uid_of_slot[k_new]);   // the label (replicas keep reading the input copy)
                 }
                 mvpar ^= 1;
+                mvcount += 1;
             } else if (p.writer && warp >= 8) {
                 // D <= 2 (the statistics of a component are not a whole number of 16-byte granules): per-thread global
                 // reductions (warps 8..11 the removal, 12..15 the addition), issued behind the move's last barrier
