@@ -15,9 +15,13 @@
 //   2. cluster barrier (hardware: barrier.cluster arrive.release / wait.acquire);
 //   3. CTA 0 scans the K + 1 choices and draws (utils.py:7-20), and writes the result into every CTA's shared memory;
 //   4. cluster barrier;
-//   5. the owner(s) of the two touched components apply the rank-one update of B (Sherman-Morrison), the mean, the
-//      scalars, and send the bit-exact statistics change to global memory with TMA bulk reductions.
-// Two cluster barriers per datum, no global memory on the critical path.  Records are rebuilt from the bit-exact
+//   5. the owner(s) of the two touched components apply the rank-one update of B (Sherman-Morrison), the mean and the
+//      scalars; CTA 0 appends (datum, from, to) to a move log.
+// Two cluster barriers per datum, no global memory on the critical path.  The bit-exact statistics (D (D + 1) / 2 + D
+// doubles per component: 2144 at D = 64) are not touched per move at all: k_big_replay applies the log afterwards, one CTA
+// per component with the component's statistics in registers, every element receiving the reference's -= fl(x_a x_b) /
+// += fl(x_a x_b) in chain order (gaussian_components.py:165-166, :184-185) -- the same bits, a few ms per sweep instead of
+// an L2 reduction of 2 x 2144 doubles inside every step (measured: 55 us per move through TMA reductions).  Records are rebuilt from the bit-exact
 // statistics at every launch (k_big_prep), and a launch covers at most BIG_SPAN data, which bounds the drift of the
 // incrementally updated records like REFRESH_EVERY does in bgmm_fast.cuh.
 #pragma once
@@ -86,7 +90,7 @@ struct BSh {
     // CTA-local
     double wtot[4];
     double gam, den, rk;
-    long long moves, evals, steps;
+    long long moves, evals, steps, n_log;
     unsigned long long margin_bits;
     int K, stop;
 };
@@ -98,7 +102,6 @@ template <int DP> struct BSmem {
     double *qloc;     // LMAX
     double *ebuf;     // KCH: exp(weight - reference) of every choice (used in CTA 0)
     double *vbuf;     // DP: v = B d of the component being updated
-    double *dlt;      // 2 x (PP + DP): statistics deltas for the TMA (parity buffers)
     double *xb, *ub, *lpb;
     long long *ib;
     int *uidb, *kob;
@@ -127,7 +130,6 @@ template <int DP> __device__ inline BSmem<DP> big_carve(double *base, int K_max)
     s.qloc = q; q += L::LMAX;
     s.ebuf = q; q += KCH;
     s.vbuf = q; q += DP;
-    s.dlt = q; q += 2 * (L::PP + DP);
     s.xb = q; q += SB * DP;
     s.ub = q; q += SB;
     s.lpb = q; q += SB;
@@ -180,7 +182,8 @@ template <int DP> __device__ __forceinline__ double bsym(const double *__restric
 // the sweep kernel: one cluster per chain
 // ---------------------------------------------------------------------------------------------
 template <int DP>
-__global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const double *__restrict__ rec_in, long long pos_limit) {
+__global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const double *__restrict__ rec_in, long long pos_limit,
+                                                    int4 *__restrict__ mlog) {
     using L = BL<DP>;
     constexpr int C = L::C, NL = L::NL, R = L::R;
     extern __shared__ __align__(16) double smem_raw[];
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
     const int K = __ldcg(&ctl->K);
     const int Lc = (K > c) ? (K - c + C - 1) / C : 0;     // components this CTA owns: k = l * C + c
     if (tid == 0) {
-        sh.K = K; sh.stop = 0; sh.moves = sh.evals = sh.steps = 0;
+        sh.K = K; sh.stop = 0; sh.moves = sh.evals = sh.steps = 0; sh.n_log = 0;
         const double one = 1.0;
         sh.margin_bits = (unsigned long long)__double_as_longlong(one);
         sh.res_k = 0; sh.res_rare = 0; sh.res_mg = 1.0;
@@ -223,7 +226,6 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
     cluster_sync_all();   // every CTA's shared memory is initialised before anyone stores into it remotely
 
     const uint32_t ebuf0 = map_to_cta(s.ebuf, 0);       // CTA 0's choice buffer
-    int mvpar = 0;
     long long pos = p.start_pos;
     bool stop = false;
     while (pos < pos_limit && !stop) {
@@ -389,19 +391,7 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
                     sh.den = den;
                     sh.rk = (side ? -1.0 : 1.0) / (p.k0 + n2);   // m' = m -+ d / kappa(n2), d = m - x
                 }
-                // statistics deltas for the TMA (gaussian_components.py:165-166, :184-185: -+ fl(x_a x_b), -+ x_a)
-                double *db = s.dlt + (size_t)mvpar * (L::PP + DP);
-                if (tid == 32) {   // the previous group that read this buffer has long completed; wait for it anyway
-                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                }
                 __syncthreads();
-                for (int e = tid; e < L::PP + DP; e += TB) {
-                    double v;
-                    if (e < L::PP) { const int a = s.rc[e] >> 8, b = s.rc[e] & 0xff; v = __dmul_rn(x[a], x[b]); }
-                    else v = x[e - L::PP];
-                    db[e] = side ? v : -v;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // each writer, in front of the TMA's read
                 const double gam = sh.gam, rk = sh.rk;
                 // rank-one update of the triangle in its storage order: index = j * NL + lane
                 for (int idx = tid; idx < L::PP; idx += TB) {
@@ -424,16 +414,12 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
                     sc[F_CWO] = cn0 - 0.5 * lds;
                 }
                 __syncthreads();
-                if (tid == 32) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    fast::seq_bulk_add(p.S + (size_t)k * L::PP, db, L::PP);
-                    fast::seq_bulk_add(p.num + (size_t)k * DP, db + L::PP, DP);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                mvpar ^= 1;
             }
             if (c == 0 && tid == 0) {
-                __stcg(p.z_uid + s.ib[jj], s.uid_of_slot[k_new]);   // one writer, no replicas: the labels change in place
+                const long long i = s.ib[jj];
+                __stcg(p.z_uid + i, s.uid_of_slot[k_new]);   // one writer, no replicas: the labels change in place
+                __stcg(mlog + sh.n_log, make_int4((int)i, k_old, k_new, 0));   // the statistics follow from the log
+                sh.n_log += 1;
                 sh.moves += 1;
             }
         }
@@ -441,12 +427,12 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
     }
 
     // ---- epilogue ----
-    if (tid == 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncthreads();
     for (int l = tid; l < Lc; l += TB) __stcg(p.counts + (l * C + c), (long long)s.rec[(size_t)l * R + L::SC + F_N]);
     if (c == 0 && tid == 0) {
         __stcg(&ctl->pos, pos);
         __stcg(&ctl->error, stop ? E_RARE : 0);
+        __stcg(&ctl->win, sh.n_log);   // entries of the move log (Ctl::win is idle in this engine)
         __stcg(&ctl->moves, __ldcg(&ctl->moves) + sh.moves);
         __stcg(&ctl->evals, __ldcg(&ctl->evals) + sh.evals);
         __stcg(&ctl->seq_data, __ldcg(&ctl->seq_data) + sh.steps);
@@ -454,6 +440,82 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
         atomicMin(&ctl->margin_bits, sh.margin_bits);
     }
     cluster_sync_all();   // no CTA exits while another may still store into its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------
+// The bit-exact sufficient statistics from the move log: CTA k holds component k's statistics in registers (EPT elements
+// per thread: S packed row-major, then num), scans the log in chain order and applies, for every move that touches k,
+//     S_ab -= fl(x_a x_b), num_a -= x_a   (the datum leaves: del_item, gaussian_components.py:184-185)
+//     S_ab += fl(x_a x_b), num_a += x_a   (it joins: add_item, :165-166)
+// one rounded multiply and one rounded add per element, in the order the chain made the moves: the reference's bits.
+// Matching entries are gathered a tile at a time and their rows of X fetched G at a time, so the row loads overlap.
+// ---------------------------------------------------------------------------------------------
+template <int DP> __global__ void __launch_bounds__(256) k_big_replay(const Params p, const int4 *__restrict__ mlog, long long n_log) {
+    using L = BL<DP>;
+    constexpr int T = 256, NS = L::PP + DP, EPT = (NS + T - 1) / T, TILE = 1024, G = 8;
+    __shared__ int4 ent[TILE];
+    __shared__ int hit[TILE];          // matching entries of the tile: (index in tile) << 1 | joins
+    __shared__ int nhit;
+    __shared__ double xs[G][DP];
+    __shared__ unsigned short rc[L::PP];
+    const int k = blockIdx.x, tid = threadIdx.x;
+    for (int e = tid; e < L::PP; e += T) {
+        int a, b;
+        decode_row_idx(e, a, b);
+        rc[e] = (unsigned short)((a << 8) | b);
+    }
+    double *S = p.S + (size_t)k * L::PP, *num = p.num + (size_t)k * DP;
+    double acc[EPT];
+    int ea[EPT], eb[EPT];
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < EPT; ++t) {
+        const int e = tid + t * T;
+        acc[t] = 0.0; ea[t] = 0; eb[t] = -1;
+        if (e < L::PP) { acc[t] = S[e]; ea[t] = rc[e] >> 8; eb[t] = rc[e] & 0xff; }
+        else if (e < NS) { acc[t] = num[e - L::PP]; ea[t] = e - L::PP; eb[t] = -1; }
+    }
+    for (long long base = 0; base < n_log; base += TILE) {
+        const int nt = (int)min((long long)TILE, n_log - base);
+        __syncthreads();
+        if (tid == 0) nhit = 0;
+        for (int t = tid; t < nt; t += T) ent[t] = mlog[base + t];
+        __syncthreads();
+        if (tid == 0) {   // chain order is kept by a serial gather (a tile is 1024 entries; matches are ~2 %)
+            int n = 0;
+            for (int t = 0; t < nt; ++t) {
+                const int4 m = ent[t];
+                if (m.y == k) hit[n++] = t << 1;
+                if (m.z == k) hit[n++] = (t << 1) | 1;
+            }
+            nhit = n;
+        }
+        __syncthreads();
+        const int nh = nhit;
+        for (int h0 = 0; h0 < nh; h0 += G) {
+            const int ng = min(G, nh - h0);
+            __syncthreads();
+            for (int t = tid; t < ng * DP; t += T) {
+                const int g = t / DP, a = t % DP;
+                xs[g][a] = p.X[(size_t)ent[hit[h0 + g] >> 1].x * DP + a];
+            }
+            __syncthreads();
+            for (int g = 0; g < ng; ++g) {
+                const bool joins = hit[h0 + g] & 1;
+#pragma unroll
+                for (int t = 0; t < EPT; ++t) {
+                    const double o = eb[t] >= 0 ? __dmul_rn(xs[g][ea[t]], xs[g][eb[t]]) : xs[g][ea[t]];
+                    acc[t] = joins ? __dadd_rn(acc[t], o) : __dsub_rn(acc[t], o);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < EPT; ++t) {
+        const int e = tid + t * T;
+        if (e < L::PP) S[e] = acc[t];
+        else if (e < NS) num[e - L::PP] = acc[t];
+    }
 }
 
 }  // namespace big

@@ -349,7 +349,7 @@ static void free_all(bgmm_handle *h) {
     cudaFree(h->d_counts); cudaFree(h->d_num); cudaFree(h->d_S); cudaFree(h->d_rec); cudaFree(h->d_wbuf);
     cudaFree(h->d_rec_prior); cudaFree(h->d_ctl); cudaFree(h->d_err); cudaFree(h->d_u); cudaFree(h->d_order);
     cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf);
-    cudaFree(h->d_true); cudaFree(h->d_table); cudaFree(h->d_pv); cudaFree(h->d_recBig);
+    cudaFree(h->d_true); cudaFree(h->d_table); cudaFree(h->d_pv); cudaFree(h->d_recBig); cudaFree(h->d_mlog);
     // buffers shared with the chains forked from / with this one: freed with the last of them
     if (h->sb && --h->sb->refs == 0) {
         SharedBufs *b = h->sb;
@@ -832,6 +832,9 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
             CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             pos = c.pos;
+            // the bit-exact statistics follow from the launch's move log (one CTA per component, chain order)
+            if (int rc = h->ops->big_replay(h, p, c.K, c.win)) return rc;
+            c.win = 0;
             if (c.error == big::E_RARE) {
                 // the generic engine's (Cholesky) records follow from the statistics; its step resolves the datum
                 c.error = 0;

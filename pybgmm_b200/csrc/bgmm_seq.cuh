@@ -331,7 +331,6 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     double *dbuf = ntb + 24;
     // move counter of the last bulk group that touched each component (the issuing thread's bookkeeping)
     int *lastmv = reinterpret_cast<int *>(dbuf + 4 * NSP);
-    if (tid < SEQ_KMAX) lastmv[tid] = -1000;
     int mvcount = 0;
     int mvpar = 0;
     const bool bulk = BULK && !(p.tune & 16);   // developer switch: bit 4 = per-thread reductions instead of the TMA
@@ -340,6 +339,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     // warp -> (part, group of 32 components): see seq_part_of_warp; this thread's component is k
     const int grp = seq_group_of_warp(warp);
     const int k = grp * 32 + lane;
+    if (tid < SEQ_KMAX) lastmv[tid] = -1000;
     double *col = rec + k;
     const double *mu = col + Ly::MU * ST;
     double *sc = col + Ly::SC * ST;
