@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
         int done = 0;
         for (int jj = 0; jj < nb; ++jj) {
             const int k_old = s.kob[jj];
-            if (k_old < 0) { stop = true; break; }      // an unassigned datum: the general step (same decision in every CTA)
+            if (k_old < 0) { stop = true; if (tid == 0) sh.res_rare = 5; break; }   // an unassigned datum: the general step
             const double *x = s.xb + jj * DP;
             const double wref = p.log_alpha + s.lpb[jj];
             // ---- 1. quadratic forms and weights of the components this CTA owns ----
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
                     const unsigned who = __ballot_sync(0xffffffffu, upper > t0);
                     if (who != 0u && lane == __ffs(who) - 1) {
                         k_new = kk;
-                        mg = (double)__fdividef((float)fmin(t0 - lower, upper - t0), (float)tot);
+                        mg = margin_ratio(fmin(t0 - lower, upper - t0), tot);
                         have = true;
                     }
                 }
@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
                 if (have) {
                     // anything but a stay or a plain move between two live components ends the launch: a birth, a draw
                     // inside the margin guard, an untrusted closed form / a component that would die (NaN), overflow
-                    const int rare = (!(tot > 0.0) || !(tot < INFINITY) || k_new >= K || mg < p.guard) ? 1 : 0;
+                    // (the code says why: 1 sum not finite / positive, 2 birth, 3 margin guard, 4 NaN weight)
+                    const int rare = (tot != tot) ? 4 : (!(tot > 0.0) || !(tot < INFINITY)) ? 1 : (k_new >= K) ? 2 : (mg < p.guard) ? 3 : 0;
                     for (int t = 0; t < C; ++t) {
                         st_remote_f64(map_to_cta(&sh.res_mg, t), mg);
                         st_remote_u32(map_to_cta(&sh.res_k, t), (unsigned)k_new);
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
         __stcg(&ctl->pos, pos);
         __stcg(&ctl->error, stop ? E_RARE : 0);
         __stcg(&ctl->win, sh.n_log);   // entries of the move log (Ctl::win is idle in this engine)
+        if (stop) __stcg(&ctl->prof[sh.res_rare & 7], __ldcg(&ctl->prof[sh.res_rare & 7]) + 1);   // why it was handed back
         __stcg(&ctl->moves, __ldcg(&ctl->moves) + sh.moves);
         __stcg(&ctl->evals, __ldcg(&ctl->evals) + sh.evals);
         __stcg(&ctl->seq_data, __ldcg(&ctl->seq_data) + sh.steps);

@@ -204,6 +204,16 @@ __device__ __forceinline__ void grid_barrier(Ctl *c) {
     __syncthreads();
 }
 
+// m / s for 0 <= m <= s, s > 0 finite, to single-precision accuracy and without a double division (whose slow path
+// is a call): both are scaled by the power of two that brings s into [1, 2) first, so sums beyond the float range
+// (unnormalised probabilities exp(weight - reference) reach e^200 at D = 64) neither overflow nor flush the quotient.
+// This is the margin of a draw in probability units -- a diagnostic and the margin guard's input.
+__device__ __forceinline__ double margin_ratio(double m, double s) {
+    const long long eb = (__double_as_longlong(s) >> 52) & 0x7ff;               // biased exponent of s
+    const double sc = __longlong_as_double((2046LL - eb) << 52);                // 2^(1023 - eb): s * sc in [1, 2)
+    return (double)__fdividef((float)(m * sc), (float)(s * sc));
+}
+
 // log count prior: crpmm.py:70 np.log(counts) / pcrpmm.py:107-108 np.log(np.power(counts, n_power))
 __device__ __forceinline__ double log_count(double n, double power) {
     if (power == 1.0) return log(n);

@@ -831,6 +831,9 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
             if (int rc = h->ops->big_sweep(h, p, std::min<long long>(h->N, pos + big::BIG_SPAN))) return rc;
             CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            if (getenv("BGMM_WPROF"))
+                fprintf(stderr, "  cluster launch from %lld to %lld: moves logged %lld, %s, K=%d\n", pos, (long long)c.pos,
+                        (long long)c.win, c.error == big::E_RARE ? "handed back" : "span done", c.K);
             pos = c.pos;
             // the bit-exact statistics follow from the launch's move log (one CTA per component, chain order)
             if (int rc = h->ops->big_replay(h, p, c.K, c.win)) return rc;

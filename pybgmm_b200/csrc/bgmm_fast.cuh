@@ -575,7 +575,7 @@ static __device__ __forceinline__ int f_warp_pick_inl(const double *__restrict__
         const int src = __ffs(who) - 1;
         k = __shfl_sync(0xffffffffu, cand, src);
         mg = __shfl_sync(0xffffffffu, mg, src);
-        mg = (double)__fdividef((float)mg, (float)s);
+        mg = margin_ratio(mg, s);
     }
     *margin = mg;
     if (!(s > 0.0) || !(s < INFINITY)) k = -2;
@@ -1220,7 +1220,7 @@ __device__ __noinline__ void f_step(const Params &p, const FSmem<DP> &s, int jj,
             const unsigned who = __ballot_sync(0xffffffffu, upper > t0);
             if (who != 0u && lane == __ffs(who) - 1) {
                 sh.wcand[warp] = tid;
-                sh.wmg[warp] = (double)__fdividef((float)fmin(t0 - lower, upper - t0), (float)tot);
+                sh.wmg[warp] = margin_ratio(fmin(t0 - lower, upper - t0), tot);
             } else if (who == 0u && lane == 0) {
                 sh.wcand[warp] = 1 << 20;
             }
@@ -1628,7 +1628,7 @@ __device__ __noinline__ void f_bulk_eval(const Params &p, const FSmem<DP> &s, lo
             if (!ok || !(ssum < INFINITY) || !(t0 >= pre) || !(t0 < pre + eown)) {
                 cand = true;
             } else {
-                const double mg = (double)__fdividef((float)fmin(t0 - pre, pre + eown - t0), (float)ssum);
+                const double mg = margin_ratio(fmin(t0 - pre, pre + eown - t0), ssum);
                 if (mg < p.guard) cand = true;   // margin guard: resolved in full by every CTA
                 else my_margin = fmin(my_margin, mg);
             }

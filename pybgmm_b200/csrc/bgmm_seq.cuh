@@ -334,6 +334,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
     int mvcount = 0;
     int mvpar = 0;
     const bool bulk = BULK && !(p.tune & 16);   // developer switch: bit 4 = per-thread reductions instead of the TMA
+    const bool stats_on = !(p.tune & 64);       // developer switch: bit 6 = no statistics at all (timing experiments only)
     const double *fmtab = smem_raw + O::FM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warp -> (part, group of 32 components): see seq_part_of_warp; this thread's component is k
@@ -433,7 +434,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                         const unsigned who = __ballot_sync(0xffffffffu, upper > t0);
                         if (who != 0u && lane == __ffs(who) - 1) {
                             sh.k_new = k;
-                            sh.last_mg = (double)__fdividef((float)fmin(t0 - lower, upper - t0), (float)tot);
+                            sh.last_mg = margin_ratio(fmin(t0 - lower, upper - t0), tot);
                         }
                     }
                     if (tid == 0) {
@@ -509,7 +510,7 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
                 }
                 seq_partial_v<DP, PART, ST>(B, col, mu, x, vp);
             }
-            if (bulk) {
+            if (bulk && stats_on) {
                 if (p.writer && warp >= 8) {
                     // the bit-exact statistics change as two delta vectors in shared memory (warps 8..11: the component
                     // the datum leaves, 12..15: the one it joins): -+ fl(x_a x_b) and -+ x_a, the reference's operands
@@ -566,7 +567,9 @@ __device__ __noinline__ int f_seq_part(const Params &p, const FSmem<DP> &s, int 
             SEQ_T(9);   // second half of the move
             bar_sync_all();                                                            // #5
             SEQ_T(10);  // wait at #5
-            if (bulk) {
+            if (!stats_on) {
+                if (p.writer && tid == 384) __stcg(p.z_out + ib[jj], s.uid_of_slot[k_new]);
+            } else if (bulk) {
                 // One thread hands the four delta vectors to the TMA: element-wise IEEE round-to-nearest adds performed at
                 // the L2 (cp.reduce.async.bulk .add.f64, SASS UBLKRED.ADD.F64.RN) -- the same bits as the reference's
                 // `+=` / `-=`, and no warp waits for them: per-thread global reductions (RED.ADD.F64) in front of a CTA
