@@ -519,7 +519,9 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": prof.get("dram_bytes"), "traffic_regime": dominant if prof else None,
                      "peak_source": peak_src,
-                     "kernel": "k_fast_sweep<%d> (one launch = one sweep)" % D if (cov == "full" and D <= 16) else "k_sweep",
+                     "kernel": ("k_fast_sweep<%d> (one launch = one sweep)" % D if (cov == "full" and D <= 16) else
+                                "k_big_sweep<%d> (thread-block cluster; a sweep is a few launches)" % D
+                                if (cov == "full" and D in (32, 64)) else "k_sweep"),
                      "algorithmic_bytes_per_eval": b_eval, "algorithmic_bytes_per_datum": b_datum,
                      "kernel_ms_per_launch": kernel_ms / K,
                      "true_bound": "latency of the sequential dependency: every datum that moves is one serial step "
