@@ -131,6 +131,20 @@ int bgmm_sweep_dev(bgmm_t *h, const int64_t *d_order, const double *d_uniforms, 
 int bgmm_fork(bgmm_t *parent, bgmm_t **out);
 int bgmm_sweep_many(bgmm_t *const *handles, int32_t n, const int64_t *const *d_orders, const double *const *d_uniforms,
                     double alpha, double power, bgmm_sweep_stats *out);
+/*
+ * replaces: one pass of the per-datum loop of CSCRPMM.constrained_gibbs_sample with the constrained re-draw
+ * (igmm/cscrpmm.py:290-358; the approximate step :418-461 is the same loop with CRP weights).  status[k] says what slot k
+ * was when the sweep started: 1 = useful cluster, 2 = non-useful cluster (cscrpmm.py:159-167), 0 = neither.  After the
+ * ordinary draw, a datum whose old slot is non-useful draws again -- same probabilities, the next uniform of the stream
+ * (utils.draw, utils/utils.py:7-20) -- until the slot drawn is a useful one (:344-347); any other datum goes back to its
+ * old slot index (:349).  `uniforms` is the random.random() stream from the sweep's first draw on, n_uniforms >= N values;
+ * *consumed returns how many were used (so the caller can leave the interpreter's generator exactly where the
+ * reference's loop would have).  Runs datum by datum on the generic engine (the number of uniforms a datum consumes
+ * depends on the draws before it).  BGMM_EINVAL if the stream runs out.
+ */
+int bgmm_sweep_constrained(bgmm_t *h, const int64_t *order, const double *uniforms, int64_t n_uniforms, double alpha,
+                           double power, const int32_t *status, int32_t n_status, int64_t *consumed,
+                           bgmm_sweep_stats *out);
 /* Engine policy: 0 = adaptive (default), 1 = always the sequential per-datum path, 2 = always speculative windows;
  * 3..5 = the same three policies on the generic engine (any D, any K_max) instead of the shared-memory-resident one. */
 int bgmm_set_engine(bgmm_t *h, int32_t mode);

@@ -57,6 +57,8 @@ def lib():
         L.orc_log_marg.restype = C.c_double
         L.orc_log_marg.argtypes = [C.c_void_p, C.c_double]
         L.orc_sweep.argtypes = [C.c_void_p, ip, dp, C.c_double, dp, C.POINTER(SweepStats)]
+        L.orc_sweep_constrained.argtypes = [C.c_void_p, ip, dp, C.c_int64, C.c_double, dp, C.POINTER(C.c_int), C.c_int,
+                                            C.POINTER(C.c_int64), C.POINTER(SweepStats)]
         L.orc_peek_probs.argtypes = [C.c_void_p, C.c_int64, C.c_double, dp, dp, dp]
         L.orc_K.argtypes = [C.c_void_p]
         for name, rt in (("orc_z", ip), ("orc_counts", ip), ("orc_num", dp), ("orc_Sp", dp),
@@ -209,6 +211,26 @@ class Oracle(object):
         return st
 
 
+    def sweep_constrained(self, uniforms, alpha, status, order=None, logcount_tab=None):
+        """One sweep with CSCRPMM's constrained re-draw (cscrpmm.py:342-350, :455-461).  status[k]: 1 useful, 2 non-useful
+        slot at the start of the sweep.  `uniforms` is the random.random() stream from the sweep's first draw on; returns
+        (SweepStats, number of uniforms consumed)."""
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        o = None if order is None else np.ascontiguousarray(order, dtype=np.int64)
+        t = None if logcount_tab is None else np.ascontiguousarray(logcount_tab, dtype=np.float64)
+        sv = np.ascontiguousarray(status, dtype=np.int32)
+        st = SweepStats()
+        used = C.c_int64()
+        rc = lib().orc_sweep_constrained(self._h, None if o is None else _ip(o), _dp(u), len(u), float(alpha),
+                                         None if t is None else _dp(t), sv.ctypes.data_as(C.POINTER(C.c_int)), len(sv),
+                                         C.byref(used), C.byref(st))
+        if rc == -2:
+            raise RuntimeError("the uniform stream ran out")
+        if rc != 0:
+            raise IndexError("K_max overflow (the reference raises IndexError in add_item)")
+        return st, used.value
+
+
 # ---------------------------------------------------------------------------
 # Reference-shaped drivers: consume the *global* random / np.random state the
 # way the reference does, so a seeded run is comparable with the shimmed
@@ -272,4 +294,60 @@ def run_adapcrpmm(orc, n_iter, alpha, r_up=1.3, adapcrp_perct=0.04, adapcrp_burn
         u = np.array([random.random() for _ in range(orc.N)])
         use_power = flag_adapcrp and i_iter > adapcrp_burnin
         stats.append(orc.sweep(u, alpha, order=order, logcount_tab=logcount_table(orc.N, power) if use_power else None))
+    return stats
+
+
+def _status_from_counts(counts, K, threshold, K_max):
+    """cscrpmm.py:159-167 / :425-432: slots with more than `threshold` members are useful (1), the others non-useful
+    (2); slots that do not exist yet are neither (0)."""
+    st = np.zeros(K_max + 1, dtype=np.int32)
+    st[:K] = np.where(np.asarray(counts[:K]) > threshold, 1, 2)
+    return st
+
+
+def _constrained_sweep(orc, alpha, status, order, tab):
+    """One constrained sweep consuming the global `random` stream exactly as the reference would: one random.random()
+    per datum plus one per re-draw (utils.py:15)."""
+    state = random.getstate()
+    L = 400 * orc.N + 4096      # a datum far from every useful cluster re-draws many times (1 / P(useful) on average)
+    u = np.array([random.random() for _ in range(L)])
+    st, used = orc.sweep_constrained(u, alpha, status, order=order, logcount_tab=tab)
+    random.setstate(state)
+    for _ in range(used):
+        random.random()
+    return st
+
+
+def run_cscrpmm(orc, n_iter, alpha, flag_constrain=False, n_constrain=1000000, thres=0., flag_power=False, n_power=1,
+                power_burnin=100000, flag_approx=False, approx_thres_perct=0., approx_burnin=1000000,
+                flag_adapcrp_form2=False, r_up=1., adapcrp_perct=0., adapcrp_burnin=1000000):
+    """cscrpmm.py:96-485 with num_saved=0, for the flags the CUDA path supports (constrained re-draw, powered scan,
+    per-sweep adaptive power, approximate step)."""
+    stats = []
+    N = orc.N
+    for i_iter in range(n_iter):
+        constrained = False
+        status = None
+        if flag_constrain and i_iter % n_constrain == 0:
+            constrained = True
+            status = _status_from_counts(orc.counts, orc.K, N * thres, orc.K_max)
+        power = 1.0
+        if flag_adapcrp_form2 and i_iter > adapcrp_burnin:
+            n_k = np.array(orc.counts[:orc.K])
+            small = len(n_k[np.where(n_k <= N * adapcrp_perct)[0]]) * 1.0 / len(n_k)
+            power_form2 = 1.0 + (r_up - 1.0) * small
+        order = np.random.permutation(range(N)) if (flag_power and n_power > 1) else None
+        if flag_power and i_iter > power_burnin:
+            power = n_power
+        elif flag_adapcrp_form2 and i_iter > adapcrp_burnin:
+            power = power_form2
+        tab = logcount_table(N, power) if power != 1.0 else None
+        if constrained:
+            stats.append(_constrained_sweep(orc, alpha, status, order, tab))
+        else:
+            u = np.array([random.random() for _ in range(N)])
+            stats.append(orc.sweep(u, alpha, order=order, logcount_tab=tab))
+        if flag_approx and i_iter > approx_burnin:
+            status = _status_from_counts(orc.counts, orc.K, N * approx_thres_perct, orc.K_max)
+            stats.append(_constrained_sweep(orc, alpha, status, None, None))
     return stats

@@ -1,5 +1,6 @@
 """pybgmm_b200 -- B200-native collapsed-Gibbs sampler for the CRP / pCRP Gaussian mixture model behind the class
-surface of junlulocky/PyBGMM (NIW, GaussianComponents{,Diag}, IGMM / CRPMM / PCRPMM / ADAPCRPMM).
+surface of junlulocky/PyBGMM (NIW, FixedVarPrior, GaussianComponents{,Diag,FixedVar}, IGMM / CRPMM / PCRPMM / ADAPCRPMM /
+CSCRPMM).
 
 The package layout mirrors the reference's (`pybgmm.prior`, `pybgmm.gaussian`, `pybgmm.gmm`, `pybgmm.igmm`,
 `pybgmm.utils`), so switching is a change of the top-level package name.  All arithmetic of the hot path runs in
@@ -8,8 +9,8 @@ libbgmm_b200.so (hand-written sm_100a CUDA); there is no CPU fallback.
 from .prior import NIW
 from .gaussian import GaussianComponents, GaussianComponentsDiag, GaussianComponentsFixedVar, FixedVarPrior
 from .gmm import GMM
-from .igmm import IGMM, CRPMM, PCRPMM, ADAPCRPMM
+from .igmm import IGMM, CRPMM, PCRPMM, ADAPCRPMM, CSCRPMM
 
 __all__ = ["NIW", "FixedVarPrior", "GaussianComponents", "GaussianComponentsDiag", "GaussianComponentsFixedVar", "GMM",
-           "IGMM", "CRPMM", "PCRPMM", "ADAPCRPMM"]
+           "IGMM", "CRPMM", "PCRPMM", "ADAPCRPMM", "CSCRPMM"]
 __version__ = "0.1.0"

@@ -21,7 +21,7 @@ EXPORTS = (
     "bgmm_sweep_index", "bgmm_get_state", "bgmm_get_assignments_dev", "bgmm_K", "bgmm_log_prior",
     "bgmm_log_post_pred", "bgmm_log_marg_k", "bgmm_log_marg", "bgmm_add_item", "bgmm_del_item", "bgmm_mt19937_fill",
     "bgmm_set_true_labels", "bgmm_contingency", "bgmm_cluster_ssq", "bgmm_set_label", "bgmm_set_state", "bgmm_set_guard",
-    "bgmm_fork", "bgmm_sweep_many", "bgmm_create_fixedvar",
+    "bgmm_fork", "bgmm_sweep_many", "bgmm_create_fixedvar", "bgmm_sweep_constrained",
 )
 
 
@@ -74,6 +74,8 @@ def lib():
     L.bgmm_set_assignments.argtypes = [vp, ip]
     L.bgmm_sweep.argtypes = [vp, ip, dp, C.c_double, C.c_double, C.POINTER(SweepStats)]
     L.bgmm_sweep_dev.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.POINTER(SweepStats)]
+    L.bgmm_sweep_constrained.argtypes = [vp, ip, dp, C.c_int64, C.c_double, C.c_double, C.POINTER(C.c_int32), C.c_int32,
+                                         C.POINTER(C.c_int64), C.POINTER(SweepStats)]
     L.bgmm_set_engine.argtypes = [vp, C.c_int32]
     L.bgmm_seed.argtypes = [vp, C.c_uint64]
     L.bgmm_get_uniforms.argtypes = [vp, C.c_int64, dp]
@@ -237,6 +239,19 @@ class Chain(object):
         st = SweepStats()
         _check(lib().bgmm_sweep(self._h, _ip(o), _dp(u), float(alpha), float(power), C.byref(st)))
         return st
+
+    def sweep_constrained(self, alpha, power, order, uniforms, status):
+        """One sweep with CSCRPMM's constrained re-draw (bgmm_sweep_constrained).  `uniforms`: the random.random() stream
+        from the sweep's first draw on (>= N values); `status[k]`: 1 useful / 2 non-useful slot at the start of the sweep.
+        Returns (SweepStats, number of uniforms consumed)."""
+        o = None if order is None else np.ascontiguousarray(order, dtype=np.int64)
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        sv = np.ascontiguousarray(status, dtype=np.int32)
+        st = SweepStats()
+        used = C.c_int64()
+        _check(lib().bgmm_sweep_constrained(self._h, _ip(o), _dp(u), len(u), float(alpha), float(power),
+                                            sv.ctypes.data_as(C.POINTER(C.c_int32)), len(sv), C.byref(used), C.byref(st)))
+        return st, used.value
 
     def sweep_dev(self, alpha, power=1.0, d_order=0, d_uniforms=0):
         """`d_order` / `d_uniforms`: raw device addresses (e.g. torch.Tensor.data_ptr()) or 0."""

@@ -79,6 +79,7 @@ struct Ctl {
     long long explicit_evals, refreshes;
     long long guard_hits;          // draws whose margin was below Params::guard and were redone on the exact path
     long long fast_steps;          // data resolved by the register-resident sequential step (bgmm_seq.cuh)
+    long long uextra;              // constrained sweep: uniforms consumed by re-draws so far (bgmm_sweep_constrained)
     long long watchdog_ns;         // spin loops give up (error word + trap) after this many ns of the global timer
     long long prof[16];            // phase clocks of CTA 0 (cycles), see bgmm_fast.cuh
     unsigned long long wsum[16], wcnt[16], wmax[16];  // evaluator unit clocks by category (profile builds)
@@ -132,6 +133,11 @@ struct Params {
     int *err;                 // device error word of the handle (set by set-up kernels: BGMM_E* code)
     float gap_to_win, gap_to_seq;  // mode switches of the resident engine: windows from this gap between movers up,
                               // sequential steps from this gap down (env BGMM_GAP_WIN / BGMM_GAP_SEQ)
+    // constrained re-draw (CSCRPMM, cscrpmm.py:342-350): status[k] = 1 useful / 2 non-useful slot at the start of the sweep
+    // (0: neither); uniforms are then consumed in order, u_len of them are available.  NULL: ordinary sweep.
+    const int *status;
+    int n_status;
+    long long u_len;
     int solo;                 // 1: this CTA is the chain's only replica (bgmm_sweep_many: one chain per CTA) -- grid
                               // barriers become CTA barriers, the sequential engine only
     int writer;               // set per CTA by the kernel: this CTA writes the chain's global state (CTA 0, or solo)

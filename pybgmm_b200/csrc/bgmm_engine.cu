@@ -349,7 +349,7 @@ static void free_all(bgmm_handle *h) {
     cudaFree(h->d_counts); cudaFree(h->d_num); cudaFree(h->d_S); cudaFree(h->d_rec); cudaFree(h->d_wbuf);
     cudaFree(h->d_rec_prior); cudaFree(h->d_ctl); cudaFree(h->d_err); cudaFree(h->d_u); cudaFree(h->d_order);
     cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf);
-    cudaFree(h->d_true); cudaFree(h->d_table); cudaFree(h->d_pv); cudaFree(h->d_recBig); cudaFree(h->d_mlog);
+    cudaFree(h->d_true); cudaFree(h->d_table); cudaFree(h->d_pv); cudaFree(h->d_recBig); cudaFree(h->d_mlog); cudaFree(h->d_status); cudaFree(h->d_ubig);
     // buffers shared with the chains forked from / with this one: freed with the last of them
     if (h->sb && --h->sb->refs == 0) {
         SharedBufs *b = h->sb;
@@ -761,6 +761,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     c.moves = c.births = c.deaths = c.evals = c.windows = c.seq_data = c.wasted = 0;
     c.explicit_evals = c.refreshes = 0;
     c.guard_hits = c.fast_steps = 0;
+    c.uextra = 0;
     c.watchdog_ns = h->watchdog_ns;
     memset(c.prof, 0, sizeof(c.prof));
     memset(c.wsum, 0, sizeof(c.wsum)); memset(c.wcnt, 0, sizeof(c.wcnt)); memset(c.wmax, 0, sizeof(c.wmax));
@@ -787,7 +788,9 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     }
     CU(cudaEventRecord(h->ev0, st));
     // engine 0..2: the replicated-state-machine engine (bgmm_fast.cuh) where it applies; 3..5: the generic engine
-    bool fast = h->fast_ok && h->engine < 3 && c.K <= h->Kcap;
+    const bool constrained = (h->cs_status != nullptr);   // re-draws consume a data-dependent number of uniforms: one CTA,
+    if (constrained) p.engine = 1;                        // datum by datum, on the generic engine
+    bool fast = h->fast_ok && h->engine < 3 && c.K <= h->Kcap && !constrained;
     if (fast) {
         // the replicas read the labels as they were at the start of the sweep; CTA 0 writes the other copy
         CU(cudaMemcpyAsync(h->d_z2, h->d_z, sizeof(int) * (size_t)h->N, cudaMemcpyDeviceToDevice, st));
@@ -820,7 +823,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     // draw inside the margin guard); that datum is resolved by the generic engine's step, the records are rebuilt from the
     // bit-exact statistics, and the cluster continues behind it.
     bool big_done = false;
-    if (!fast && generic_from < 0 && h->big_ok && h->engine < 3 && c.K <= h->Kcap && c.K >= 1) {
+    if (!fast && generic_from < 0 && h->big_ok && h->engine < 3 && c.K <= h->Kcap && c.K >= 1 && !constrained) {
         CU(cudaEventRecord(h->ev2, st));
         long long pos = 0;
         bool to_generic = false;
@@ -912,7 +915,9 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         out->launches = h->launches; out->sweep_kernel_ms = ms_k;
         out->guard_hits = c.guard_hits; out->fast_steps = c.fast_steps;
     }
+    h->cs_consumed = h->N + c.uextra;
     if (c.error == BGMM_EKMAX) return fail(BGMM_EKMAX, "a new component would exceed K_max (the reference raises IndexError)");
+    if (c.error == -8) return fail(BGMM_EINVAL, "constrained sweep: the uniform stream ran out (re-draws need more uniforms)");
     if (c.error != 0) return fail(c.error, "sweep: non-finite weights or covariance not positive definite");
     // the records the auxiliary entry points use were rebuilt after the sweep: report a failure of that rebuild now,
     // not from whichever call happens to look next
@@ -1075,6 +1080,35 @@ int bgmm_sweep(bgmm_t *h, const int64_t *order, const double *uniforms, double a
         d_u = h->d_u;
     }
     return run_sweep(h, d_order, d_u, alpha, power, out);
+}
+
+int bgmm_sweep_constrained(bgmm_t *h, const int64_t *order, const double *uniforms, int64_t n_uniforms, double alpha,
+                           double power, const int32_t *status, int32_t n_status, int64_t *consumed, bgmm_sweep_stats *out) {
+    if (!h || !uniforms || !status) return fail(BGMM_EINVAL, "NULL argument");
+    if (n_uniforms < h->N || n_status < 1) return fail(BGMM_EINVAL, "at least N uniforms and one status entry are needed");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (h->ubig_cap < n_uniforms) {
+        cudaFree(h->d_ubig);
+        h->d_ubig = nullptr;
+        h->ubig_cap = 0;
+        CU(cudaMalloc((void **)&h->d_ubig, sizeof(double) * (size_t)n_uniforms));
+        h->ubig_cap = n_uniforms;
+    }
+    if (!h->d_status) CU(cudaMalloc((void **)&h->d_status, sizeof(int) * (size_t)(h->K_max + 1)));
+    const int ns = std::min<int>(n_status, h->K_max + 1);
+    CU(cudaMemcpyAsync(h->d_ubig, uniforms, sizeof(double) * (size_t)n_uniforms, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_status, status, sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice, st));
+    const long long *d_order = nullptr;
+    if (order) {
+        CU(cudaMemcpyAsync(h->d_order, order, sizeof(long long) * (size_t)h->N, cudaMemcpyHostToDevice, st));
+        d_order = h->d_order;
+    }
+    h->cs_status = h->d_status; h->cs_n = ns; h->cs_ulen = n_uniforms;
+    const int rc = run_sweep(h, d_order, h->d_ubig, alpha, power, out);
+    h->cs_status = nullptr; h->cs_n = 0; h->cs_ulen = 0;
+    if (consumed) *consumed = h->cs_consumed;
+    return rc;
 }
 
 int bgmm_K(bgmm_t *h) { return h ? h->K : -1; }

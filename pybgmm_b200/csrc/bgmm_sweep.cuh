@@ -31,6 +31,7 @@ struct Sh {
     double u;
     // CTA 0's working copy of the control-block counters (loaded after barrier 1, stored before barrier 2)
     long long moves, births, deaths, evals, windows, seq_data, wasted, guard_hits;
+    long long uextra;        // constrained sweep: uniforms consumed by re-draws so far
     unsigned long long margin_bits;
     double gap;
     int n_free;
@@ -226,9 +227,16 @@ __device__ void resolve(const Params &p, const Smem &sm, long long j) {
         if (uid >= 0) { k_old = __ldcg(p.slot_of_uid + uid); n_old = __ldcg(p.counts + k_old); }
         sh.k_old = k_old; sh.n_old = n_old;
         sh.need_explicit = 0; sh.died = 0;
-        sh.u = p.u[j];
+        if (p.status) {
+            // constrained sweep: the uniforms are one stream, consumed in order (one per datum plus one per re-draw)
+            if (j + sh.uextra >= p.u_len) { sh.error = -8; sh.u = 0.5; }
+            else sh.u = p.u[j + sh.uextra];
+        } else {
+            sh.u = p.u[j];
+        }
     }
     __syncthreads();
+    if (sh.error) return;
     const long long i = sh.i;
     if (tid < DP) sm.x[tid] = p.X[(size_t)i * DP + tid];
     const int k_old = sh.k_old;
@@ -341,6 +349,52 @@ __device__ void resolve(const Params &p, const Smem &sm, long long j) {
             continue;
         }
         break;
+    }
+    if (p.status && sh.error == 0) {
+        // CSCRPMM's constrained re-draw (cscrpmm.py:342-350, :455-461): a datum whose old slot was a non-useful cluster when
+        // the sweep started draws again -- the same probabilities, a fresh uniform each time (utils.py:15) -- until the slot
+        // drawn was a useful one; any other datum goes back to its old slot index.  sm.w holds the unnormalised
+        // probabilities of the draw above.
+        if (warp == 0) {
+            const int st_old = (k_old >= 0 && k_old < p.n_status) ? p.status[k_old] : 0;
+            if (st_old == 2) {
+                const int n = K + 1;
+                const int per = (n + 31) / 32;
+                const int lo = lane * per, hi = min(n, lo + per);
+                double sl = 0.0;
+                for (int k = lo; k < hi; ++k) sl += sm.w[k];
+                double inc = sl;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const double s = __shfl_sync(0xffffffffu, inc, 31);
+                long long extra = sh.uextra;
+                int k_sel = -1;
+                while (true) {
+                    extra += 1;
+                    const long long ui = j + extra;
+                    if (ui >= p.u_len) { if (lane == 0) sh.error = -8; break; }
+                    const double u2 = p.u[ui];
+                    double t = u2 * s - (inc - sl);
+                    int cand = 0x7fffffff;
+                    for (int k = lo; k < hi; ++k) {
+                        t -= sm.w[k];
+                        if (t < 0.0) { cand = k; break; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+                    k_sel = (cand == 0x7fffffff) ? K : cand;   // utils.py:20 fallback: the last index
+                    if (k_sel < p.n_status && p.status[k_sel] == 1) break;
+                }
+                if (lane == 0) { sh.uextra = extra; sh.k_new = k_sel < 0 ? K : k_sel; }
+            } else if (lane == 0) {
+                sh.k_new = k_old;
+            }
+        }
+        __syncthreads();
+        if (sh.error) return;
     }
     const int k_new = sh.k_new;
     if (tid == 0) {
@@ -626,6 +680,7 @@ __global__ void __launch_bounds__(T_SWEEP, 1) k_sweep(const Params p) {
                 sh.evals = __ldcg(&ctl->evals); sh.windows = __ldcg(&ctl->windows);
                 sh.seq_data = __ldcg(&ctl->seq_data); sh.wasted = __ldcg(&ctl->wasted);
                 sh.guard_hits = __ldcg(&ctl->guard_hits);
+                sh.uextra = __ldcg(&ctl->uextra);
                 sh.margin_bits = __ldcg(&ctl->margin_bits); sh.gap = __ldcg(&ctl->gap);
                 sh.n_free = __ldcg(&ctl->n_free);
                 sh.n_old = __ldcg(&ctl->first);  // broadcast slot
@@ -680,6 +735,7 @@ __global__ void __launch_bounds__(T_SWEEP, 1) k_sweep(const Params p) {
                 __stcg(&ctl->evals, sh.evals); __stcg(&ctl->windows, sh.windows);
                 __stcg(&ctl->seq_data, sh.seq_data); __stcg(&ctl->wasted, sh.wasted);
                 __stcg(&ctl->guard_hits, sh.guard_hits);
+                __stcg(&ctl->uextra, sh.uextra);
                 __stcg(&ctl->margin_bits, sh.margin_bits);
                 __stcg(&ctl->n_free, sh.n_free);
                 if (sh.error) __stcg(&ctl->error, sh.error);

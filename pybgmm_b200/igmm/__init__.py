@@ -3,5 +3,6 @@ from .igmm import IGMM
 from .crpmm import CRPMM
 from .pcrpmm import PCRPMM
 from .adapcrpmm import ADAPCRPMM
+from .cscrpmm import CSCRPMM
 
-__all__ = ["IGMM", "CRPMM", "PCRPMM", "ADAPCRPMM"]
+__all__ = ["IGMM", "CRPMM", "PCRPMM", "ADAPCRPMM", "CSCRPMM"]
