@@ -570,11 +570,12 @@ def run_multi_chain(a, _lib, torch, dev, X, z0_first, prior, K_max, cov, power, 
         c.set_stream(stream.cuda_stream)
     for m, c in enumerate(chains):
         c.set_assignments(gen_data(N, D, K_true, 1, chain_seed=1 + m)[2] if m else z0_first)
-    rs = np.random.RandomState(4242)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4242)
 
-    def inputs():
-        o = torch.stack([torch.from_numpy(rs.permutation(N).astype(np.int64)) for _ in range(M)]).to(dev) if power > 1 else None
-        u = torch.from_numpy(rs.random_sample((M, N))).to(dev)
+    def inputs():   # per-chain scan orders and uniforms, generated on the device (this line is not a parity run)
+        o = torch.rand(M, N, device=dev, generator=gen).argsort(dim=1) if power > 1 else None
+        u = torch.rand(M, N, device=dev, dtype=torch.float64, generator=gen)
         return o, u
     group = _lib.ChainGroup(chains)
     o, u = inputs()
