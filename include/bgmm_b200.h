@@ -146,7 +146,9 @@ int bgmm_sweep_constrained(bgmm_t *h, const int64_t *order, const double *unifor
                            double power, const int32_t *status, int32_t n_status, int64_t *consumed,
                            bgmm_sweep_stats *out);
 /* Engine policy: 0 = adaptive (default), 1 = always the sequential per-datum path, 2 = always speculative windows;
- * 3..5 = the same three policies on the generic engine (any D, any K_max) instead of the shared-memory-resident one. */
+ * 3..5 = the same three policies on the generic engine (any D, any K_max) instead of the shared-memory-resident one;
+ * 6 = adaptive, with every sweep started on the cluster step engine (full covariance, D <= 16) instead of only the
+ * sweeps that follow a dense-mover sweep. */
 int bgmm_set_engine(bgmm_t *h, int32_t mode);
 
 /* Philox stream used when uniforms == NULL: seed it, and replay the stream of a given sweep index on the host

@@ -213,7 +213,7 @@ class Chain(object):
 
     def set_engine(self, mode):
         _check(lib().bgmm_set_engine(self._h, {"adaptive": 0, "sequential": 1, "windows": 2, "generic": 3, "generic-sequential": 4,
-                                                 "generic-windows": 5}.get(mode, mode)))
+                                                 "generic-windows": 5, "cluster": 6}.get(mode, mode)))
 
     def seed(self, seed):
         _check(lib().bgmm_seed(self._h, int(seed)))

@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
 // Matching entries are gathered a tile at a time and their rows of X fetched G at a time, so the row loads overlap.
 // ---------------------------------------------------------------------------------------------
 template <int DP> __global__ void __launch_bounds__(256) k_big_replay(const Params p, const int4 *__restrict__ mlog, long long n_log) {
-    using L = BL<DP>;
+    using L = fast::Lay<DP>;   // any padded D (bgmm_clu.cuh replays through this kernel too)
     constexpr int T = 256, NS = L::PP + DP, EPT = (NS + T - 1) / T, TILE = 1024, G = 8;
     __shared__ int4 ent[TILE];
     __shared__ int hit[TILE];          // matching entries of the tile: (index in tile) << 1 | joins

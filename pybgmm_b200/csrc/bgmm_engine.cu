@@ -349,7 +349,7 @@ static void free_all(bgmm_handle *h) {
     cudaFree(h->d_counts); cudaFree(h->d_num); cudaFree(h->d_S); cudaFree(h->d_rec); cudaFree(h->d_wbuf);
     cudaFree(h->d_rec_prior); cudaFree(h->d_ctl); cudaFree(h->d_err); cudaFree(h->d_u); cudaFree(h->d_order);
     cudaFree(h->d_tmp_ll); cudaFree(h->d_recB); cudaFree(h->d_recB_prior); cudaFree(h->d_z2); cudaFree(h->d_mvbuf);
-    cudaFree(h->d_true); cudaFree(h->d_table); cudaFree(h->d_pv); cudaFree(h->d_recBig); cudaFree(h->d_mlog); cudaFree(h->d_status); cudaFree(h->d_ubig);
+    cudaFree(h->d_true); cudaFree(h->d_table); cudaFree(h->d_pv); cudaFree(h->d_recBig); cudaFree(h->d_recClu); cudaFree(h->d_mlog); cudaFree(h->d_status); cudaFree(h->d_ubig);
     // buffers shared with the chains forked from / with this one: freed with the last of them
     if (h->sb && --h->sb->refs == 0) {
         SharedBufs *b = h->sb;
@@ -558,6 +558,7 @@ static int create_impl(const double *X, int64_t N, int32_t D, int32_t cov_type, 
     if (b->d_tau) CU(cudaMemcpy(b->d_tau, h->tauv.data(), sizeof(double) * DP, cudaMemcpyHostToDevice));
     if (int rc = h->ops->fast_setup(h)) { free_all(h); delete h; return rc; }
     if (int rc = h->ops->big_setup(h)) { free_all(h); delete h; return rc; }
+    if (int rc = h->ops->clu_setup(h)) { free_all(h); delete h; return rc; }
     if (int rc = alloc_chain_state(h)) { free_all(h); delete h; return rc; }
 
     // uploads
@@ -624,6 +625,7 @@ int bgmm_fork(bgmm_t *parent, bgmm_t **out) {
     h->d_m0 = b->d_m0; h->d_S0 = b->d_S0; h->d_tau = b->d_tau;
     if (int rc = h->ops->fast_setup(h)) { free_all(h); delete h; return rc; }
     if (int rc = h->ops->big_setup(h)) { free_all(h); delete h; return rc; }
+    if (int rc = h->ops->clu_setup(h)) { free_all(h); delete h; return rc; }
     if (int rc = alloc_chain_state(h)) { free_all(h); delete h; return rc; }
     // the prior's generic record (bgmm_log_prior's source) is per handle: copy the parent's
     CU(cudaMemcpy(h->d_rec_prior, parent->d_rec_prior, sizeof(double) * h->ops->rec_len, cudaMemcpyDeviceToDevice));
@@ -649,7 +651,7 @@ int bgmm_set_stream(bgmm_t *h, void *cuda_stream) {
 }
 
 int bgmm_set_engine(bgmm_t *h, int32_t mode) {
-    if (!h || mode < 0 || mode > 5) return fail(BGMM_EINVAL, "engine mode must be in 0..5");
+    if (!h || mode < 0 || mode > 6) return fail(BGMM_EINVAL, "engine mode must be in 0..6");
     h->engine = mode;
     return 0;
 }
@@ -790,15 +792,91 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     // engine 0..2: the replicated-state-machine engine (bgmm_fast.cuh) where it applies; 3..5: the generic engine
     const bool constrained = (h->cs_status != nullptr);   // re-draws consume a data-dependent number of uniforms: one CTA,
     if (constrained) p.engine = 1;                        // datum by datum, on the generic engine
-    bool fast = h->fast_ok && h->engine < 3 && c.K <= h->Kcap && !constrained;
-    if (fast) {
+    const bool resident = h->engine < 3 || h->engine == 6;   // 6: adaptive, the cluster step engine wherever it applies
+    bool fast = h->fast_ok && resident && c.K <= h->Kcap && !constrained;
+    // Cluster engines: full covariance on padded D = 32 / 64 (bgmm_big.cuh, the whole sweep) and the cluster step engine
+    // for D <= 16 (bgmm_clu.cuh) while the movers are dense.  A launch walks the chain until the sweep ends, BIG_SPAN data
+    // are done, a component has taken its share of rank-one changes, or a datum needs the general step (a birth, a death,
+    // an explicit removal, a draw inside the margin guard); that datum is resolved by the generic engine's step, the
+    // records are rebuilt from the bit-exact statistics, and the cluster continues behind it.  The step engine hands the
+    // rest of the sweep to the resident engine's windows as soon as a span shows sparse movers.
+    const bool use_big = !fast && h->big_ok && resident && c.K <= h->Kcap && c.K >= 1 && !constrained;
+    const bool use_clu = fast && h->clu_ok && c.K >= 1 && c.K <= clu::KCH - 1 &&
+                         (h->engine == 6 || (h->engine == 0 && h->last_gap < h->clu_gap));
+    bool big_done = false;
+    bool events_on = false;
+    long long resume_at = 0;   // the resident engine starts here when the step engine handed over
+    if (use_big || use_clu) {
+        CU(cudaEventRecord(h->ev2, st));
+        events_on = true;
+        long long pos = 0;
+        bool to_generic = false, to_fast = false;
+        long long span = use_clu ? 8192 : big::BIG_SPAN;   // a short first span: the regime shows early
+        while (pos < h->N) {
+            p.start_pos = pos;
+            if (int rc = use_clu ? h->ops->clu_prep(h, p, c.K) : h->ops->big_prep(h, p, c.K)) return rc;
+            if (int rc = check_dev_err(h, "sweep (record set-up)")) return rc;
+            const long long lim = std::min<long long>(h->N, pos + span);
+            const long long moves_before = c.moves;
+            if (int rc = use_clu ? h->ops->clu_sweep(h, p, lim) : h->ops->big_sweep(h, p, lim)) return rc;
+            CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (getenv("BGMM_WPROF"))
+                fprintf(stderr, "  cluster launch from %lld to %lld: moves logged %lld, %s, K=%d\n", pos, (long long)c.pos,
+                        (long long)c.win, c.error == big::E_RARE ? "handed back" : "span done", c.K);
+            const long long walked = c.pos - pos, moved = c.moves - moves_before;
+            pos = c.pos;
+            span = big::BIG_SPAN;
+            // the bit-exact statistics follow from the launch's move log (one CTA per component, chain order)
+            if (int rc = h->ops->big_replay(h, p, c.K, c.win)) return rc;
+            c.win = 0;
+            if (c.error == big::E_RARE) {
+                // the generic engine's (Cholesky) records follow from the statistics; its step resolves the datum
+                c.error = 0;
+                CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
+                if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
+                h->launches += 1;
+                if (int rc = h->ops->resolve_one(h, p, pos)) return rc;
+                CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                pos = c.pos;
+                if (c.error != 0) break;
+                if (c.K < 1 || c.K > (use_clu ? clu::KCH - 1 : h->Kcap)) { to_generic = true; break; }
+            } else if (c.error != 0) {
+                break;
+            }
+            if (use_clu && h->engine == 0 && walked >= 4096 && pos < h->N &&
+                (double)walked / (double)(moved + 1) >= 2.0 * h->clu_gap) {
+                to_fast = true;   // sparse movers: speculative windows are the better engine for the rest of the sweep
+                break;
+            }
+        }
+        if (use_clu && (to_generic || to_fast) && pos < h->N && c.error == 0 && c.K <= h->Kcap) {
+            resume_at = pos;      // the resident engine finishes the sweep (it also holds more components)
+            p.init_gap = (double)h->N;   // ... starting in window mode
+        } else if (to_generic && pos < h->N) {
+            CU(cudaEventRecord(h->ev3, st));
+            generic_from = pos;   // more live components than the cluster holds: the generic engine finishes the sweep
+            fast = false;
+        } else {
+            CU(cudaEventRecord(h->ev3, st));
+            big_done = true;
+            fast = false;
+            if (c.error == 0 && c.K > 0) {
+                if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
+                h->launches += 1;
+            }
+        }
+    }
+    if (fast && !big_done) {
         // the replicas read the labels as they were at the start of the sweep; CTA 0 writes the other copy
         CU(cudaMemcpyAsync(h->d_z2, h->d_z, sizeof(int) * (size_t)h->N, cudaMemcpyDeviceToDevice, st));
+        p.start_pos = resume_at;
         if (int rc = h->ops->fast_prep(h, p, c.K)) return rc;
         // a component whose S_N is not positive definite stops the sweep here, before the kernel would run on a
         // partially written record
         if (int rc = check_dev_err(h, "sweep (record set-up)")) return rc;
-        CU(cudaEventRecord(h->ev2, st));
+        if (!events_on) CU(cudaEventRecord(h->ev2, st));
         if (int rc = h->ops->fast_sweep(h, p)) return rc;
         CU(cudaEventRecord(h->ev3, st));
         h->launches += 1;
@@ -816,56 +894,6 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
             c.error = 0; c.bar_count = 0;
             CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
             fast = false;
-        }
-    }
-    // engine 0..2 on padded D = 32 / 64, full covariance: the cluster engine (bgmm_big.cuh).  A launch walks the chain until
-    // the sweep ends, BIG_SPAN data are done, or a datum needs the general step (a birth, a death, an explicit removal, a
-    // draw inside the margin guard); that datum is resolved by the generic engine's step, the records are rebuilt from the
-    // bit-exact statistics, and the cluster continues behind it.
-    bool big_done = false;
-    if (!fast && generic_from < 0 && h->big_ok && h->engine < 3 && c.K <= h->Kcap && c.K >= 1 && !constrained) {
-        CU(cudaEventRecord(h->ev2, st));
-        long long pos = 0;
-        bool to_generic = false;
-        while (pos < h->N) {
-            p.start_pos = pos;
-            if (int rc = h->ops->big_prep(h, p, c.K)) return rc;
-            if (int rc = check_dev_err(h, "sweep (record set-up)")) return rc;
-            if (int rc = h->ops->big_sweep(h, p, std::min<long long>(h->N, pos + big::BIG_SPAN))) return rc;
-            CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            if (getenv("BGMM_WPROF"))
-                fprintf(stderr, "  cluster launch from %lld to %lld: moves logged %lld, %s, K=%d\n", pos, (long long)c.pos,
-                        (long long)c.win, c.error == big::E_RARE ? "handed back" : "span done", c.K);
-            pos = c.pos;
-            // the bit-exact statistics follow from the launch's move log (one CTA per component, chain order)
-            if (int rc = h->ops->big_replay(h, p, c.K, c.win)) return rc;
-            c.win = 0;
-            if (c.error == big::E_RARE) {
-                // the generic engine's (Cholesky) records follow from the statistics; its step resolves the datum
-                c.error = 0;
-                CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
-                if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
-                h->launches += 1;
-                if (int rc = h->ops->resolve_one(h, p, pos)) return rc;
-                CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
-                CU(cudaStreamSynchronize(st));
-                pos = c.pos;
-                if (c.error != 0) break;
-                if (c.K > h->Kcap || c.K < 1) { to_generic = true; break; }
-            } else if (c.error != 0) {
-                break;
-            }
-        }
-        CU(cudaEventRecord(h->ev3, st));
-        if (to_generic && pos < h->N) {
-            generic_from = pos;   // more live components than the cluster holds: the generic engine finishes the sweep
-        } else {
-            big_done = true;
-            if (c.error == 0 && c.K > 0) {
-                if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
-                h->launches += 1;
-            }
         }
     }
     const bool ran_fast = fast || generic_from >= 0 || big_done;

@@ -1,0 +1,9 @@
+#!/bin/bash
+# cluster step engine: parity tests, then the per-sweep probe on C3 / C2 shapes
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_clu.py -x -q --timeout 300 --timeout-method=thread > gpurun_out/pytest_clu.log 2>&1
+echo "pytest rc=$?"; tail -15 gpurun_out/pytest_clu.log | cut -c1-300
+timeout 300 python tools/perf_probe.py --N 1000000 --D 16 --K 100 --sweeps 4 > gpurun_out/probe_clu_c3.log 2>&1; echo "probe rc=$?"
+grep -E "^sweep" gpurun_out/probe_clu_c3.log | cut -c1-420
+timeout 300 python tools/perf_probe.py --N 100000 --D 2 --K 30 --sweeps 3 --power 1.0 > gpurun_out/probe_clu_c2.log 2>&1; echo "probe rc=$?"
+grep -E "^sweep" gpurun_out/probe_clu_c2.log | cut -c1-420
