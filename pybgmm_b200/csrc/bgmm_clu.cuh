@@ -43,17 +43,30 @@ constexpr int REFRESH_CAP = 2048;    // rank-one changes of one component per la
 #define BGMM_CLU_C 16
 #endif
 
+#ifdef BGMM_PROFILE
+#define CLU_TDECL long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tlast = clock64()
+#define CLU_T(slot) do { const long long now_ = clock64(); tacc[slot] += now_ - tlast; tlast = now_; } while (0)
+#define CLU_TFLUSH(row) do { if (lane == 0) for (int t_ = 0; t_ < 8; ++t_) __stcg(&ctl->tprof[row][t_], __ldcg(&ctl->tprof[row][t_]) + tacc[t_]); } while (0)
+#else
+#define CLU_TDECL do { } while (0)
+#define CLU_T(slot) do { } while (0)
+#define CLU_TFLUSH(row) do { } while (0)
+#endif
+
 template <int DP> struct CL {
     static constexpr int PP = DP * (DP + 1) / 2;
     static constexpr int MU = PP, SC = PP + DP, R = PP + DP + NSC;
-    static constexpr int C = BGMM_CLU_C;                 // CTAs per cluster
-    static constexpr int WPC = KCH / C;                  // component warps per CTA
+    static constexpr int C = BGMM_CLU_C;                 // CTAs per cluster: rank 0 draws, ranks 1 .. C - 1 hold the components
+    static constexpr int CC = C - 1;                     // component CTAs
+    static constexpr int WPC = (KCH + CC - 1) / CC;      // component warps per CTA
     static constexpr int NW = WPC + 2;                   // + the producer warp + the draw warp (active in the leader)
     static constexpr int TB = NW * 32;
-    static constexpr int G = (32 / DP < DP) ? 32 / DP : DP;   // lanes per row of B
+    // a component occupies both halves of its warp: lanes 0..15 evaluate it as it is, lanes 16..31 as it would be after
+    // the datum in flight changed it; within a half, row a of B sits in lanes a G .. a G + G - 1, CP columns each
+    static constexpr int G = (16 / DP < DP) ? 16 / DP : DP;   // lanes per row of B
     static constexpr int CP = DP / G;                    // columns per lane
-    static constexpr int ACT = DP * G;                   // lanes that hold matrix elements
-    static_assert(G * CP == DP && ACT <= 32, "rows must tile a warp");
+    static constexpr int ACT = DP * G;                   // lanes of a half that hold matrix elements
+    static_assert(G * CP == DP && ACT <= 16, "rows must tile half a warp");
 };
 
 // ---- mbarrier / DSMEM primitives ----
@@ -80,6 +93,55 @@ __device__ __forceinline__ unsigned mbar_try_wait_cluster(void *bar, unsigned pa
     return ok;
 }
 // 8 bytes into the shared memory of a CTA of the cluster, completing 8 bytes on that CTA's mbarrier
+// 1 / a for a normal positive a: the hardware's single-precision estimate (2^-22) and two Newton steps (2^-44, 2^-88)
+__device__ __forceinline__ double recip2(double a) {
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)a));
+    double r = (double)rf;
+    r = fma(r, fma(-a, r, 1.0), r);
+    r = fma(r, fma(-a, r, 1.0), r);
+    return r;
+}
+// fm::f_log / fm::f_exp with the polynomials in Estrin form: the same tables, arguments and accuracy, four / two
+// dependent operations fewer on the chain every step waits for
+__device__ __forceinline__ double c_log(double x, const double *__restrict__ tab) {
+    const long long bits = __double_as_longlong(x);
+    const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);  // [1, 2)
+    const int i = (int)((bits >> (52 - 7)) & (fm::LOG_N - 1));
+    const double inv = tab[2 * i], lc = tab[2 * i + 1];
+    const double r = fma(m, inv, -1.0);                 // |r| <= 2^-8
+    // log1p(r) = r + r^2 P(r),  P = -1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7 - r^6/8
+    const double r2 = r * r;
+    const double pa = fma(r, 1.0 / 3.0, -1.0 / 2.0), pb = fma(r, 1.0 / 5.0, -1.0 / 4.0), pc = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    const double r4 = r2 * r2;
+    const double P = fma(r4, fma(r2, -1.0 / 8.0, pc), fma(r2, pb, pa));
+    const double l1p = fma(r2, P, r);
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double ed = (double)e;
+    return fma(ed, LN2_HI, lc) + fma(ed, LN2_LO, l1p);
+}
+__device__ __forceinline__ double c_exp(double t, const double *__restrict__ tab) {
+    const double INV = 9.23324826168936568e+01;          // 64 / ln 2
+    const double C_HI = 1.08304244931787252e-02;         // ln2 / 64, high part (27 trailing zero bits)
+    const double C_LO = 2.03070420217029510e-10;         //           low part
+    const double kd = rint(t * INV);
+    const int k = (int)kd;
+    double r = fma(-kd, C_HI, t);
+    r = fma(-kd, C_LO, r);                               // |r| <= ln2/128
+    // exp(r) - 1 = r + r^2 Q(r),  Q = 1/2 + r/6 + r^2/24 + r^3/120 + r^4/720
+    const double r2 = r * r;
+    const double qa = fma(r, 1.0 / 6.0, 0.5), qb = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    const double Q = fma(r2, fma(r2, 1.0 / 720.0, qb), qa);
+    const double pm1 = fma(r2, Q, r);
+    const double sv = tab[2 * fm::LOG_N + (k & (fm::EXP_N - 1))];
+    const double v = fma(sv, pm1, sv);                   // 2^(j/64) * exp(r)
+    const int q = k >> 6;                                // floor division: k = 64 q + j
+    const int q1 = q / 2, q2 = q - q1;
+    const double s1 = __longlong_as_double((long long)(q1 + 1023) << 52);
+    const double s2 = __longlong_as_double((long long)(q2 + 1023) << 52);
+    return (v * s1) * s2;
+}
 __device__ __forceinline__ void st_async_u64(uint32_t remote_addr, unsigned long long v, uint32_t remote_bar) {
     asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(v),
                  "r"(remote_bar) : "memory");
@@ -92,6 +154,7 @@ template <int DP> struct alignas(16) CSh {
     long long ir[RS];                 //       datum index
     int kor[RS];                      //       the component it sits in (-1: unassigned)
     int uidk[KCH];                    // leader: uid of every live slot (labels are uids)
+    double vx[CL<DP>::WPC][DP];       // per component warp: v = B d of the datum in flight, for the rank-one update
     double fm[fm::TAB_LEN];
     unsigned long long full[2], empty[2];   // ring hand-over (producer -> consumers -> producer)
     unsigned long long ebar;          // leader: K weights have arrived
@@ -138,14 +201,15 @@ template <int DP>
 __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, const double *__restrict__ rec_in, long long pos_limit,
                                                              int4 *__restrict__ mlog) {
     using L = CL<DP>;
-    constexpr int C = L::C, G = L::G, CP = L::CP, R = L::R;
+    constexpr int C = L::C, CC = L::CC, G = L::G, CP = L::CP, R = L::R;
     __shared__ CSh<DP> S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Ctl *ctl = p.ctl;
     const int c = (int)cluster_rank();
     const int K = __ldcg(&ctl->K);
     const long long j0 = p.start_pos, j1 = pos_limit;
-    const int n_comp_warps = (K > c) ? min(L::WPC, (K - c + C - 1) / C) : 0;   // live component warps of this CTA
+    // component k: warp k / CC of CTA 1 + k % CC (the leader CTA keeps its SM for the draw warp)
+    const int n_comp_warps = (c >= 1 && K > c - 1) ? min(L::WPC, (K - (c - 1) + CC - 1) / CC) : 0;   // live component warps here
     const int n_cons = n_comp_warps + (c == 0 ? 1 : 0);                        // warps that read the ring
 
     // ---- prologue ----
@@ -164,10 +228,10 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
     __syncthreads();
     cluster_sync_all();   // every CTA's barriers and buffers exist before anyone stores into them remotely
 
-    const bool is_comp = warp < n_comp_warps;
+    const long long total = j1 - j0;
+    const bool is_comp = warp < n_comp_warps && total > 0;
     const bool is_prod = warp == L::WPC && n_cons > 0;
     const bool is_draw = warp == L::WPC + 1 && c == 0;
-    const long long total = j1 - j0;
 
     if (is_prod) {
         // ---- producer: the ring of upcoming data ----
@@ -207,9 +271,15 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
         }
     } else if (is_comp) {
         // ---- component warp: component k in registers ----
-        const int k = warp * C + c;
-        const int a = (lane < L::ACT) ? lane / G : 0, h = (lane < L::ACT) ? lane % G : 0;
-        const bool act = lane < L::ACT;
+        // While the draw of datum s is in flight the warp prepares datum s + 1 under BOTH outcomes it can see: its
+        // component unchanged (lanes 0..15), and changed by datum s (lanes 16..31: removed if s sits in it, added
+        // otherwise).  One instruction stream evaluates both; the scalar tails (log, exp) run once, different instances
+        // in different lanes.  When the result arrives, the matching weight is sent at once: the chain's critical path
+        // holds no evaluation at all.
+        const int k = warp * CC + (c - 1);
+        const int half = lane >> 4, hl = lane & 15;
+        const bool act = hl < L::ACT;
+        const int a = act ? hl / G : 0, h = act ? hl % G : 0;
         const double *rk_g = rec_in + (size_t)k * R;
         double B[CP], mb[CP];
 #pragma unroll
@@ -220,101 +290,177 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             mb[t] = __ldcg(rk_g + L::MU + b);
         }
         double ma = __ldcg(rk_g + L::MU + a);
-        double sc[NSC];
-#pragma unroll
-        for (int t = 0; t < NSC; ++t) sc[t] = __ldcg(rk_g + L::SC + t);
-        const long long nt_len = (p.N + 1) * NT_W;
-        auto fetch_rows = [&](double n) -> double {   // lane l: word l of the count-table rows n - 2 .. n + 1
-            const long long idx = ((long long)n - 2) * NT_W + lane;
-            return (idx >= 0 && idx < nt_len) ? __ldg(p.ntab + idx) : 0.0;
+        double n = __ldcg(rk_g + L::SC + F_N), lds = __ldcg(rk_g + L::SC + F_LDS);
+        // window of the count table: rows wc - 8 .. wc + 7, lane l holds (l & 1 ? RK : CN) of row wc - 8 + l / 2
+        const long long nt_rows = p.N + 1;
+        auto fetch_win = [&](long long c0) -> double {
+            const long long row = c0 - 8 + (lane >> 1);
+            return (row >= 0 && row < nt_rows) ? __ldg(p.ntab + row * NT_W + ((lane & 1) ? NT_RK : NT_CN)) : 0.0;
         };
-        double trow = fetch_rows(sc[F_N]);
+        long long wc = (long long)n, wc2 = 0;
+        double tw = fetch_win(wc), tw2 = 0.0;
+        int pend = 0;   // steps until the requested window tw2 replaces tw (the load has two steps to land)
+        const double hh0 = 0.5 * (double)(p.v0 + 1);   // H(n) = (nu + D) / 2 = (v0 + 1 + n) / 2
+        // everything in a record that depends on the count alone (bgmm_fast.cuh NT_*), from the window; nn may differ
+        // between the halves
+        struct NS { double cn_n, cn_m, g, beta, hh; };
+        auto nscal = [&](double nn) -> NS {
+            const int r = (int)((long long)nn - (wc - 8));   // row of nn inside the window
+            NS o;
+            o.cn_n = __shfl_sync(0xffffffffu, tw, (2 * r) & 31);
+            o.cn_m = __shfl_sync(0xffffffffu, tw, (2 * r - 2) & 31);
+            o.g = 1.0 - __shfl_sync(0xffffffffu, tw, (2 * r + 3) & 31);      // kappa / (kappa + 1) = 1 - 1 / kappa(n + 1)
+            o.beta = 1.0 + __shfl_sync(0xffffffffu, tw, (2 * r - 1) & 31);   // kappa / (kappa - 1) = 1 + 1 / kappa(n - 1)
+            o.hh = hh0 + 0.5 * nn;
+            return o;
+        };
+        NS ns_st = nscal(n);
         const uint32_t e_dst = map_to_cta(&S.ebuf[k], 0), e_bar = map_to_cta(&S.ebar, 0);
         const bool armer = (warp == 0);
+        double *vx = S.vx[warp];
         SpinWatch wd;
-        for (long long j = j0; j < j1; ++j) {
-            const long long s = j - j0;
-            const int slot = (int)(s & (RS - 1));
-            if ((s & 31) == 0) {
-                const long long ch = s >> 5;
+        CLU_TDECL;
+        // The datum in ring slot `slot1` under this half's version of the component, WITHOUT forming the changed matrix:
+        //   B' = B + gam v v',  m' = m + rk (m - x_s),  d = m' - x1:   B' d = B d + gam (v' d) v,   d' B' d = d' B d + gam (v' d)^2
+        // so the reciprocal inside gam runs beside the matrix-vector product instead of in front of it.
+        // rk_e = gam_e = 0: the component as it is.  Returns q1 = d' B' d (uniform in the half), v1 = (B' d)[row of the lane].
+        auto quad = [&](double gam_e, double rk_e, double v_s, int slot_s, int slot1, double &q1, double &v1) {
+            double u0 = 0.0, u1 = 0.0;   // two partial chains
+#pragma unroll
+            for (int t = 0; t < CP; ++t) {
+                const int b = h * CP + t;
+                const double d1 = fma(mb[t] - S.xr[slot_s][b], rk_e, mb[t]) - S.xr[slot1][b];
+                if (t & 1) u1 = fma(B[t], d1, u1);
+                else u0 = fma(B[t], d1, u0);
+            }
+            double w = u0 + u1;
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+            const double da1 = fma(ma - S.xr[slot_s][a], rk_e, ma) - S.xr[slot1][a];
+            double qp = act ? da1 * w : 0.0, sp = act ? da1 * v_s : 0.0;
+#pragma unroll
+            for (int o = G; o < 16; o <<= 1) {
+                qp += __shfl_xor_sync(0xffffffffu, qp, o);
+                sp += __shfl_xor_sync(0xffffffffu, sp, o);
+            }
+            const double gs = gam_e * sp;
+            q1 = fma(gs, sp, qp);
+            v1 = fma(gs, v_s, w);
+        };
+
+        // datum 0
+        while (!mbar_try_wait(&S.full[0], 0u)) wd.poll(ctl, 12);
+        double cur_q, cur_v;
+        {
+            quad(0.0, 0.0, 0.0, 0, 0, cur_q, cur_v);
+            double sc[NSC];
+            sc[F_N] = n; sc[F_LDS] = lds; sc[F_CNT] = 0.0;
+            sc[F_CW] = ns_st.cn_n - 0.5 * lds; sc[F_CWO] = ns_st.cn_m - 0.5 * lds;
+            sc[F_G] = ns_st.g; sc[F_BETA] = ns_st.beta; sc[F_H] = ns_st.hh;
+            const int own0 = (k == S.kor[0]) ? 1 : 0;
+            double e = fast::f_finish_weight<1>(sc, cur_q, own0, p.log_alpha + S.lpr[0], S.fm);
+            if (own0 && n == 1.0) e = NAN;   // the datum is its component's last member: the general step
+            if (lane == 0) st_async_u64(e_dst, (unsigned long long)__double_as_longlong(e), e_bar);
+        }
+        for (long long s = 0; s < total; ++s) {
+            const int slot = (int)(s & (RS - 1)), slot1 = (int)((s + 1) & (RS - 1));
+            const bool has_next = s + 1 < total;
+            const int ko = S.kor[slot];
+            if (pend && --pend == 0) { tw = tw2; wc = wc2; }
+            if (s > 0 && (s & 31) == 0) {   // done with the previous half of the ring (its last datum was committed)
+                if (lane == 0) mbar_arrive(&S.empty[((s - 1) >> 5) & 1]);
+            }
+            if (has_next && ((s + 1) & 31) == 0) {
+                const long long ch = (s + 1) >> 5;
                 while (!mbar_try_wait(&S.full[ch & 1], (unsigned)((ch >> 1) & 1))) wd.poll(ctl, 12);
             }
-            // d = m - x, v = B d, q = d' B d
-            const double xa = S.xr[slot][a];
-            const double lp = S.lpr[slot];
-            const int ko = S.kor[slot];
-            double db[CP];
-#pragma unroll
-            for (int t = 0; t < CP; ++t) db[t] = mb[t] - S.xr[slot][h * CP + t];
-            const double da = ma - xa;
-            double v = 0.0;
-#pragma unroll
-            for (int t = 0; t < CP; ++t) v = fma(B[t], db[t], v);
-#pragma unroll
-            for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            double q = act ? da * v : 0.0;
-#pragma unroll
-            for (int o = G; o < 32; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-            const int own = (k == ko) ? 1 : 0;
-            const double wref = p.log_alpha + lp;
-            double e = fast::f_finish_weight<1>(sc, q, own, wref, S.fm);
-            if (own && sc[F_N] == 1.0) e = NAN;   // the datum is its component's last member: the general step
-            if (lane == 0) st_async_u64(e_dst, (unsigned long long)__double_as_longlong(e), e_bar);
-            if ((s & 31) == 31 || j == j1 - 1) {   // done with this half of the ring
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.empty[(s >> 5) & 1]);
+            CLU_T(0);   // ring
+            // The other outcome of datum s for this component: it left (side 0, s sits here) / it joined (side 1).
+            // del_item / add_item as a rank-one change of S_N (gaussian_components.py:154-186): Sherman-Morrison on B,
+            // the determinant lemma on log|S_N|; cur_q, cur_v: the datum's quadratic form and B d under the component
+            // as it is.
+            const int side = (k == ko) ? 0 : 1;
+            const bool alt_ok = side || n > 1.0;
+            const double beta = side ? ns_st.g : ns_st.beta;
+            const double den = side ? fma(beta, cur_q, 1.0) : fma(-beta, cur_q, 1.0);
+            const double rd = recip2(den);
+            const double gam = side ? -(beta * rd) : beta * rd;
+            const double n2 = alt_ok ? n + (side ? 1.0 : -1.0) : n;
+            const double n_mine = half ? n2 : n;
+            const NS nsx = nscal(n_mine);
+            const int r2 = (int)((long long)n2 - (wc - 8));
+            const double rkk = __shfl_sync(0xffffffffu, tw, (2 * r2 + 1) & 31);
+            const double rk = side ? -rkk : rkk;   // m' = m -+ d / kappa(n2), d = m - x
+            double e_u = 0.0, e_a = 0.0, q1 = 0.0, v1 = 0.0, al_lds = lds;
+            {
+                int own1 = 0;
+                double wref1 = 0.0, x = den;
+                if (has_next) {
+                    quad(half ? gam : 0.0, half ? rk : 0.0, cur_v, slot, slot1, q1, v1);
+                    own1 = (k == S.kor[slot1]) ? 1 : 0;
+                    wref1 = p.log_alpha + S.lpr[slot1];
+                    const double arg = own1 ? fma(-nsx.beta, q1, 1.0) : fma(nsx.g, q1, 1.0);
+                    x = (hl == 2) ? den : arg;
+                }
+                // one logarithm for the three arguments (the two weights' and the determinant lemma's), one exponential
+                const double Lg = c_log(x, S.fm);
+                al_lds = lds + __shfl_sync(0xffffffffu, Lg, 2);
+                if (has_next) {
+                    const double lds_mine = half ? al_lds : lds;
+                    const double cc = (own1 ? nsx.cn_m : nsx.cn_n) - 0.5 * lds_mine, hh = own1 ? 1.0 - nsx.hh : nsx.hh;
+                    const double tt = (cc - hh * Lg) - wref1;
+                    double e = (tt < EXP_CUTOFF) ? 0.0 : c_exp(tt, S.fm);
+                    // the own component's closed form is not trusted / the datum is its last member: the general step
+                    if (own1 && (!(x > OM_MIN) || n_mine == 1.0)) e = NAN;
+                    e_u = __shfl_sync(0xffffffffu, e, 0);
+                    e_a = alt_ok ? __shfl_sync(0xffffffffu, e, 16) : NAN;
+                }
             }
-            // the draw
+            CLU_T(1);   // preparation of datum s + 1
+            // the draw of datum s
             while (!mbar_try_wait_cluster(&S.rbar, (unsigned)(s & 1))) wd.poll(ctl, 13);
             const unsigned long long res = *(volatile unsigned long long *)&S.res;
             __syncwarp();
             if (armer && lane == 0) mbar_arrive_expect_tx(&S.rbar, 8);   // next phase
             const int k_new = (int)(res & 0xffffu), rare = (int)((res >> 16) & 0xffu), stop_after = (int)((res >> 24) & 1u);
             if (rare) break;
-            if (k_new != ko && (k == ko || k == k_new)) {
-                // the datum moves and this component is one of the two: del_item / add_item as a rank-one change of S_N
-                // (gaussian_components.py:154-186) -- Sherman-Morrison on B, the determinant lemma on log|S_N|
-                const int side = (k == k_new) ? 1 : 0;
-                const double beta = side ? sc[F_G] : sc[F_BETA];
-                const double den = side ? fma(beta, q, 1.0) : fma(-beta, q, 1.0);
-                const double rd = fast::seq_recip(den);
-                const double gam = side ? -(beta * rd) : beta * rd;
-                const int base = side ? 16 : 0;   // rows (n2 - 1, n2) of the new count n2 = n -+ 1 inside trow
-                const double cn0 = __shfl_sync(0xffffffffu, trow, base + NT_CN);
-                const double cn1 = __shfl_sync(0xffffffffu, trow, base + 8 + NT_CN);
-                const double g1 = __shfl_sync(0xffffffffu, trow, base + 8 + NT_G);
-                const double h1 = __shfl_sync(0xffffffffu, trow, base + 8 + NT_H);
-                const double b1 = __shfl_sync(0xffffffffu, trow, base + 8 + NT_BETA);
-                const double rkk = __shfl_sync(0xffffffffu, trow, base + 8 + NT_RK);
-                const double rk = side ? -rkk : rkk;   // m' = m -+ d / kappa(n2), d = m - x
-                const double gv = gam * v;
+            const bool touched = (k_new != ko) && (k == ko || k == k_new);
+            if (has_next && !stop_after && lane == 0)
+                st_async_u64(e_dst, (unsigned long long)__double_as_longlong(touched ? e_a : e_u), e_bar);
+            CLU_T(2);   // waiting for the draw
+            if (touched) {
+                // every lane adopts the other outcome: B += gam v v', m += rk (m - x_s)
+                __syncwarp();
+                if (half == 0 && act && h == 0) vx[a] = cur_v;
+                __syncwarp();
+                const double gv = gam * cur_v;
 #pragma unroll
                 for (int t = 0; t < CP; ++t) {
-                    const double vb = __shfl_sync(0xffffffffu, v, ((h * CP + t) * G) & 31);
-                    B[t] = fma(gv, vb, B[t]);
-                    mb[t] = fma(db[t], rk, mb[t]);
+                    const int b = h * CP + t;
+                    B[t] = fma(gv, vx[b], B[t]);
+                    mb[t] = fma(mb[t] - S.xr[slot][b], rk, mb[t]);
                 }
-                ma = fma(da, rk, ma);
-                const double n2 = sc[F_N] + (side ? 1.0 : -1.0);
-                const double lds = sc[F_LDS] + fm::f_log(den, S.fm);
-                sc[F_N] = n2;
-                sc[F_LDS] = lds;
-                sc[F_CW] = cn1 - 0.5 * lds;
-                sc[F_G] = g1;
-                sc[F_H] = h1;
-                sc[F_BETA] = b1;
-                sc[F_CWO] = cn0 - 0.5 * lds;
-                trow = fetch_rows(n2);
+                ma = fma(ma - S.xr[slot][a], rk, ma);
+                n = n2;
+                lds = al_lds;
+                ns_st = nscal(n);
+                const long long n_now = (long long)n;
+                if (pend == 0 && (n_now - wc >= 3 || wc - n_now >= 3)) { wc2 = n_now; tw2 = fetch_win(n_now); pend = 2; }
+                CLU_T(3);   // commit
             }
+            cur_q = __shfl_sync(0xffffffffu, q1, touched ? 16 : 0);
+            cur_v = __shfl_sync(0xffffffffu, v1, (touched ? 16 : 0) + hl);
             if (stop_after) break;
         }
+        if (warp == 0 && c <= 2) CLU_TFLUSH(c);
+        if (warp == n_comp_warps - 1 && c == 1) CLU_TFLUSH(3);
         if (armer && lane == 0) S.stop = 1;
-        if (lane == 0) __stcg(p.counts + k, (long long)sc[F_N]);
+        if (lane == 0) __stcg(p.counts + k, (long long)n);
     } else if (is_draw) {
         // ---- the draw warp of the leader CTA ----
         uint32_t r_dst = 0, r_bar = 0;
-        const int n_cta = min(C, K);            // CTAs that own components
-        if (lane < n_cta) { r_dst = map_to_cta(&S.res, lane); r_bar = map_to_cta(&S.rbar, lane); }
+        const int n_cta = min(CC, K);           // CTAs that own components: ranks 1 .. n_cta
+        if (lane < n_cta) { r_dst = map_to_cta(&S.res, lane + 1); r_bar = map_to_cta(&S.rbar, lane + 1); }
         int cnt[4] = {0, 0, 0, 0};
         long long moves = 0, steps = 0, n_log = 0, pos = j1;
         unsigned long long margin_bits;
@@ -322,7 +468,9 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
         int why = 0;
         bool stopped = false, pending_stop = false;
         SpinWatch wd;
+        CLU_TDECL;
         for (long long j = j0; j < j1; ++j) {
+            CLU_T(2);   // bookkeeping of the previous step
             const long long s = j - j0;
             const int slot = (int)(s & (RS - 1));
             if (lane == 0) mbar_arrive_expect_tx(&S.ebar, (unsigned)K * 8u);
@@ -334,6 +482,7 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             const int ko = S.kor[slot];
             const long long i = S.ir[slot];
             while (!mbar_try_wait_cluster(&S.ebar, (unsigned)(s & 1))) wd.poll(ctl, 15);
+            CLU_T(0);   // waiting for the weights
             // crpmm.py:75-78, utils.py:7-20: the first choice whose cumulative weight exceeds u * total
             double e[4];
             asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e[0]), "=d"(e[1]) : "r"(smem_u32(&S.ebuf[4 * lane])) : "memory");
@@ -386,6 +535,7 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             const unsigned long long word = (unsigned long long)(unsigned)(k_new & 0xffff) | ((unsigned long long)rare << 16) |
                                             ((unsigned long long)stop_after << 24);
             if (lane < n_cta) st_async_u64(r_dst, word, r_bar);
+            CLU_T(1);   // scan + draw
             // ---- off the critical path from here ----
             double mg = 0.0;
             if (who != 0u) mg = __shfl_sync(0xffffffffu, margin_ratio(gapw, tot), src);
@@ -418,7 +568,9 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             }
             if (stop_after) { pos = j + 1; break; }
         }
+        CLU_TFLUSH(0);
         if (lane == 0) {
+            S.stop = 1;   // this CTA's producer
             __stcg(&ctl->pos, pos);
             __stcg(&ctl->error, stopped ? E_RARE : 0);
             __stcg(&ctl->win, n_log);   // entries of the move log (Ctl::win is idle in this engine)

@@ -926,6 +926,9 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         out->explicit_evals = c.explicit_evals; out->refreshes = c.refreshes; out->generic_from = generic_from;
         for (int t = 0; t < 16; ++t) out->phase_cycles[t] = c.prof[t];
         if (getenv("BGMM_WPROF")) {
+            fprintf(stderr, "  cluster step timeline: draw warp wait-weights=%lld scan+draw=%lld post=%lld | comp(cta0,w0) ring=%lld eval=%lld wait=%lld upd=%lld | comp(cta1,w0) ring=%lld eval=%lld wait=%lld upd=%lld | comp(cta0,last) ring=%lld eval=%lld wait=%lld upd=%lld\n",
+                    c.tprof[0][0], c.tprof[0][1], c.tprof[0][2], c.tprof[1][0], c.tprof[1][1], c.tprof[1][2], c.tprof[1][3],
+                    c.tprof[2][0], c.tprof[2][1], c.tprof[2][2], c.tprof[2][3], c.tprof[3][0], c.tprof[3][1], c.tprof[3][2], c.tprof[3][3]);
             static const char *tn[11] = {"stage", "A", "wait1", "finish+scan", "wait2", "draw", "wait3", "move-a", "wait4",
                                          "move-b", "wait5"};
             for (int pt = 0; pt < 4; ++pt) {
