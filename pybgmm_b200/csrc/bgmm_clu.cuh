@@ -39,6 +39,7 @@ constexpr int KCH = 128;             // choices (K + 1) the draw warp holds: 4 p
 constexpr int RS = 64;               // ring slots: two halves of 32 data
 constexpr int E_RARE = 2;            // internal: the datum at Ctl::pos needs the general step
 constexpr int REFRESH_CAP = 2048;    // rank-one changes of one component per launch
+constexpr float PRE_MARGIN = 1e-4f;  // single-precision draw: accepted when the target is this far (x total) from a boundary
 #ifndef BGMM_CLU_C
 #define BGMM_CLU_C 16
 #endif
@@ -61,12 +62,10 @@ template <int DP> struct CL {
     static constexpr int WPC = (KCH + CC - 1) / CC;      // component warps per CTA
     static constexpr int NW = WPC + 2;                   // + the producer warp + the draw warp (active in the leader)
     static constexpr int TB = NW * 32;
-    // a component occupies both halves of its warp: lanes 0..15 evaluate it as it is, lanes 16..31 as it would be after
-    // the datum in flight changed it; within a half, row a of B sits in lanes a G .. a G + G - 1, CP columns each
-    static constexpr int G = (16 / DP < DP) ? 16 / DP : DP;   // lanes per row of B
+    static constexpr int G = (32 / DP < DP) ? 32 / DP : DP;   // lanes per row of B
     static constexpr int CP = DP / G;                    // columns per lane
-    static constexpr int ACT = DP * G;                   // lanes of a half that hold matrix elements
-    static_assert(G * CP == DP && ACT <= 16, "rows must tile half a warp");
+    static constexpr int ACT = DP * G;                   // lanes that hold matrix elements
+    static_assert(G * CP == DP && ACT <= 32, "rows must tile a warp");
 };
 
 // ---- mbarrier / DSMEM primitives ----
@@ -88,8 +87,13 @@ __device__ __forceinline__ unsigned mbar_try_wait(void *bar, unsigned parity) {
 // the phase was completed by st.async writes of another CTA of the cluster: acquire at cluster scope
 __device__ __forceinline__ unsigned mbar_try_wait_cluster(void *bar, unsigned parity) {
     unsigned ok;
+#ifdef BGMM_CLU_ACQ_CTA
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#else
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
     return ok;
 }
 // 8 bytes into the shared memory of a CTA of the cluster, completing 8 bytes on that CTA's mbarrier
@@ -272,14 +276,18 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
     } else if (is_comp) {
         // ---- component warp: component k in registers ----
         // While the draw of datum s is in flight the warp prepares datum s + 1 under BOTH outcomes it can see: its
-        // component unchanged (lanes 0..15), and changed by datum s (lanes 16..31: removed if s sits in it, added
-        // otherwise).  One instruction stream evaluates both; the scalar tails (log, exp) run once, different instances
-        // in different lanes.  When the result arrives, the matching weight is sent at once: the chain's critical path
-        // holds no evaluation at all.
+        // component unchanged, and changed by datum s (removed if s sits in it, added otherwise).  The changed
+        // component is never formed: with v = B d_s, q_s = d_s' B d_s of datum s (kept from its own evaluation),
+        //     B' = B + gam v v',   m' = m + rk d_s,   d' = d + rk d_s   (d = m - x_{s+1})
+        //     sigma = v' d' = v' d + rk q_s
+        //     d'' B' d' = d' B d + rk (2 v' d + rk q_s) + gam sigma^2,       B' d' = B d + (rk + gam sigma) v
+        // so ONE matrix-vector product serves both outcomes, and the scalar tails (log, exp) run once with the two
+        // outcomes in different lanes.  When the result arrives the matching weight is sent at once: the chain's
+        // critical path holds no evaluation at all.
         const int k = warp * CC + (c - 1);
-        const int half = lane >> 4, hl = lane & 15;
-        const bool act = hl < L::ACT;
-        const int a = act ? hl / G : 0, h = act ? hl % G : 0;
+        const bool act = lane < L::ACT;
+        const int a = act ? lane / G : 0, h = act ? lane % G : 0;
+        const int sel = lane & 3;   // scalar tails: 0 the component as it is, 1 the other outcome, 2 the determinant lemma
         const double *rk_g = rec_in + (size_t)k * R;
         double B[CP], mb[CP];
 #pragma unroll
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
         int pend = 0;   // steps until the requested window tw2 replaces tw (the load has two steps to land)
         const double hh0 = 0.5 * (double)(p.v0 + 1);   // H(n) = (nu + D) / 2 = (v0 + 1 + n) / 2
         // everything in a record that depends on the count alone (bgmm_fast.cuh NT_*), from the window; nn may differ
-        // between the halves
+        // from lane to lane
         struct NS { double cn_n, cn_m, g, beta, hh; };
         auto nscal = [&](double nn) -> NS {
             const int r = (int)((long long)nn - (wc - 8));   // row of nn inside the window
@@ -320,39 +328,34 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
         double *vx = S.vx[warp];
         SpinWatch wd;
         CLU_TDECL;
-        // The datum in ring slot `slot1` under this half's version of the component, WITHOUT forming the changed matrix:
-        //   B' = B + gam v v',  m' = m + rk (m - x_s),  d = m' - x1:   B' d = B d + gam (v' d) v,   d' B' d = d' B d + gam (v' d)^2
-        // so the reciprocal inside gam runs beside the matrix-vector product instead of in front of it.
-        // rk_e = gam_e = 0: the component as it is.  Returns q1 = d' B' d (uniform in the half), v1 = (B' d)[row of the lane].
-        auto quad = [&](double gam_e, double rk_e, double v_s, int slot_s, int slot1, double &q1, double &v1) {
+        // w = (B d)[row of the lane], q = d' B d, sg = v_s' d for the datum in ring slot `slot1` (d = m - x)
+        auto quad = [&](double v_s, int slot1, double &q1, double &sg1, double &w) {
             double u0 = 0.0, u1 = 0.0;   // two partial chains
 #pragma unroll
             for (int t = 0; t < CP; ++t) {
-                const int b = h * CP + t;
-                const double d1 = fma(mb[t] - S.xr[slot_s][b], rk_e, mb[t]) - S.xr[slot1][b];
+                const double d1 = mb[t] - S.xr[slot1][h * CP + t];
                 if (t & 1) u1 = fma(B[t], d1, u1);
                 else u0 = fma(B[t], d1, u0);
             }
-            double w = u0 + u1;
+            w = u0 + u1;
 #pragma unroll
             for (int o = 1; o < G; o <<= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-            const double da1 = fma(ma - S.xr[slot_s][a], rk_e, ma) - S.xr[slot1][a];
-            double qp = act ? da1 * w : 0.0, sp = act ? da1 * v_s : 0.0;
+            const double da1 = ma - S.xr[slot1][a];
+            q1 = act ? da1 * w : 0.0;
+            sg1 = act ? da1 * v_s : 0.0;
 #pragma unroll
-            for (int o = G; o < 16; o <<= 1) {
-                qp += __shfl_xor_sync(0xffffffffu, qp, o);
-                sp += __shfl_xor_sync(0xffffffffu, sp, o);
+            for (int o = G; o < 32; o <<= 1) {
+                q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+                sg1 += __shfl_xor_sync(0xffffffffu, sg1, o);
             }
-            const double gs = gam_e * sp;
-            q1 = fma(gs, sp, qp);
-            v1 = fma(gs, v_s, w);
         };
 
         // datum 0
         while (!mbar_try_wait(&S.full[0], 0u)) wd.poll(ctl, 12);
         double cur_q, cur_v;
         {
-            quad(0.0, 0.0, 0.0, 0, 0, cur_q, cur_v);
+            double sg0;
+            quad(0.0, 0, cur_q, sg0, cur_v);
             double sc[NSC];
             sc[F_N] = n; sc[F_LDS] = lds; sc[F_CNT] = 0.0;
             sc[F_CW] = ns_st.cn_n - 0.5 * lds; sc[F_CWO] = ns_st.cn_m - 0.5 * lds;
@@ -375,10 +378,9 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
                 while (!mbar_try_wait(&S.full[ch & 1], (unsigned)((ch >> 1) & 1))) wd.poll(ctl, 12);
             }
             CLU_T(0);   // ring
-            // The other outcome of datum s for this component: it left (side 0, s sits here) / it joined (side 1).
-            // del_item / add_item as a rank-one change of S_N (gaussian_components.py:154-186): Sherman-Morrison on B,
-            // the determinant lemma on log|S_N|; cur_q, cur_v: the datum's quadratic form and B d under the component
-            // as it is.
+            // The other outcome of datum s for this component: it left (side 0, s sits here) / it joined (side 1):
+            // del_item / add_item as a rank-one change of S_N (gaussian_components.py:154-186), Sherman-Morrison on B,
+            // the determinant lemma on log|S_N|.
             const int side = (k == ko) ? 0 : 1;
             const bool alt_ok = side || n > 1.0;
             const double beta = side ? ns_st.g : ns_st.beta;
@@ -386,34 +388,41 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             const double rd = recip2(den);
             const double gam = side ? -(beta * rd) : beta * rd;
             const double n2 = alt_ok ? n + (side ? 1.0 : -1.0) : n;
-            const double n_mine = half ? n2 : n;
-            const NS nsx = nscal(n_mine);
+            const double n_sel = (sel == 1) ? n2 : n;
+            const NS nsx = nscal(n_sel);
             const int r2 = (int)((long long)n2 - (wc - 8));
             const double rkk = __shfl_sync(0xffffffffu, tw, (2 * r2 + 1) & 31);
-            const double rk = side ? -rkk : rkk;   // m' = m -+ d / kappa(n2), d = m - x
-            double e_u = 0.0, e_a = 0.0, q1 = 0.0, v1 = 0.0, al_lds = lds;
+            const double rk = side ? -rkk : rkk;   // m' = m -+ d_s / kappa(n2), d_s = m - x_s
+            CLU_T(4);   // scalars of the other outcome
+            double e_u = 0.0, e_a = 0.0, q_u = 0.0, q_a = 0.0, sg = 0.0, w = 0.0, al_lds = lds;
             {
                 int own1 = 0;
                 double wref1 = 0.0, x = den;
                 if (has_next) {
-                    quad(half ? gam : 0.0, half ? rk : 0.0, cur_v, slot, slot1, q1, v1);
+                    double sg_u;
+                    quad(cur_v, slot1, q_u, sg_u, w);
+                    sg = fma(rk, cur_q, sg_u);
+                    q_a = fma(gam * sg, sg, fma(rk, fma(rk, cur_q, 2.0 * sg_u), q_u));
                     own1 = (k == S.kor[slot1]) ? 1 : 0;
                     wref1 = p.log_alpha + S.lpr[slot1];
-                    const double arg = own1 ? fma(-nsx.beta, q1, 1.0) : fma(nsx.g, q1, 1.0);
-                    x = (hl == 2) ? den : arg;
+                    const double q_sel = (sel == 1) ? q_a : q_u;
+                    const double arg = own1 ? fma(-nsx.beta, q_sel, 1.0) : fma(nsx.g, q_sel, 1.0);
+                    x = (sel == 2) ? den : arg;
                 }
+                CLU_T(5);   // quadratic forms
                 // one logarithm for the three arguments (the two weights' and the determinant lemma's), one exponential
                 const double Lg = c_log(x, S.fm);
                 al_lds = lds + __shfl_sync(0xffffffffu, Lg, 2);
+                CLU_T(6);   // logarithm
                 if (has_next) {
-                    const double lds_mine = half ? al_lds : lds;
-                    const double cc = (own1 ? nsx.cn_m : nsx.cn_n) - 0.5 * lds_mine, hh = own1 ? 1.0 - nsx.hh : nsx.hh;
+                    const double lds_sel = (sel == 1) ? al_lds : lds;
+                    const double cc = (own1 ? nsx.cn_m : nsx.cn_n) - 0.5 * lds_sel, hh = own1 ? 1.0 - nsx.hh : nsx.hh;
                     const double tt = (cc - hh * Lg) - wref1;
                     double e = (tt < EXP_CUTOFF) ? 0.0 : c_exp(tt, S.fm);
                     // the own component's closed form is not trusted / the datum is its last member: the general step
-                    if (own1 && (!(x > OM_MIN) || n_mine == 1.0)) e = NAN;
+                    if (own1 && (!(x > OM_MIN) || n_sel == 1.0)) e = NAN;
                     e_u = __shfl_sync(0xffffffffu, e, 0);
-                    e_a = alt_ok ? __shfl_sync(0xffffffffu, e, 16) : NAN;
+                    e_a = alt_ok ? __shfl_sync(0xffffffffu, e, 1) : NAN;
                 }
             }
             CLU_T(1);   // preparation of datum s + 1
@@ -429,9 +438,9 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
                 st_async_u64(e_dst, (unsigned long long)__double_as_longlong(touched ? e_a : e_u), e_bar);
             CLU_T(2);   // waiting for the draw
             if (touched) {
-                // every lane adopts the other outcome: B += gam v v', m += rk (m - x_s)
+                // the component takes the other outcome: B += gam v v', m += rk (m - x_s)
                 __syncwarp();
-                if (half == 0 && act && h == 0) vx[a] = cur_v;
+                if (act && h == 0) vx[a] = cur_v;
                 __syncwarp();
                 const double gv = gam * cur_v;
 #pragma unroll
@@ -446,10 +455,13 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
                 ns_st = nscal(n);
                 const long long n_now = (long long)n;
                 if (pend == 0 && (n_now - wc >= 3 || wc - n_now >= 3)) { wc2 = n_now; tw2 = fetch_win(n_now); pend = 2; }
+                cur_v = fma(fma(gam, sg, rk), cur_v, w);   // B' d' = B d + (rk + gam sigma) v
+                cur_q = q_a;
                 CLU_T(3);   // commit
+            } else {
+                cur_v = w;
+                cur_q = q_u;
             }
-            cur_q = __shfl_sync(0xffffffffu, q1, touched ? 16 : 0);
-            cur_v = __shfl_sync(0xffffffffu, v1, (touched ? 16 : 0) + hl);
             if (stop_after) break;
         }
         if (warp == 0 && c <= 2) CLU_TFLUSH(c);
@@ -462,7 +474,7 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
         const int n_cta = min(CC, K);           // CTAs that own components: ranks 1 .. n_cta
         if (lane < n_cta) { r_dst = map_to_cta(&S.res, lane + 1); r_bar = map_to_cta(&S.rbar, lane + 1); }
         int cnt[4] = {0, 0, 0, 0};
-        long long moves = 0, steps = 0, n_log = 0, pos = j1;
+        long long moves = 0, steps = 0, n_log = 0, pos = j1, slow_draws = 0;
         unsigned long long margin_bits;
         { const double one = 1.0; margin_bits = (unsigned long long)__double_as_longlong(one); }
         int why = 0;
@@ -493,43 +505,91 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
                 if (idx == K) e[t] = 1.0;
                 else if (idx > K) e[t] = 0.0;
             }
-            const double run = (e[0] + e[1]) + (e[2] + e[3]);
-            double incl = run;
+            // First in single precision: prefix sums of <= 128 non-negative terms are good to ~1e-6 of the total, so a
+            // target at least PRE_MARGIN (1e-4) of the total away from both boundaries of the interval it falls in picks
+            // the same choice as any more accurate arithmetic -- the reference's included (utils.py:15-20).  One step in
+            // ~5000 is closer than that (or overflows a float) and takes the double precision scan below.
+            int k_new = K, rare = 0;
+            double mg = 0.0;
+            bool decided = false;
+            if (!(p.tune & 128)) {
+                const float f0 = (float)e[0], f1 = (float)e[1], f2 = (float)e[2], f3 = (float)e[3];
+                float inclf = (f0 + f1) + (f2 + f3);
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            if (lane == 0) excl = 0.0;
-            const double tot = __shfl_sync(0xffffffffu, incl, 31);
-            const double t0 = u * tot;
-            int cand = -1;
-            double lower = excl, upper = excl;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float t = __shfl_up_sync(0xffffffffu, inclf, o);
+                    if (lane >= o) inclf += t;
+                }
+                float lowf = __shfl_up_sync(0xffffffffu, inclf, 1);
+                if (lane == 0) lowf = 0.0f;
+                const float totf = __shfl_sync(0xffffffffu, inclf, 31);
+                const float t0f = (float)u * totf;
+                int candf = -1;
+                float upf = lowf;
+                const float ff[4] = {f0, f1, f2, f3};
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                if (cand < 0 && 4 * lane + t <= K) {
-                    upper = lower + e[t];
-                    if (upper > t0) cand = 4 * lane + t;
-                    else lower = upper;
+                for (int t = 0; t < 4; ++t) {
+                    if (candf < 0 && 4 * lane + t <= K) {
+                        upf = lowf + ff[t];
+                        if (upf > t0f) candf = 4 * lane + t;
+                        else lowf = upf;
+                    }
+                }
+                const unsigned whof = __ballot_sync(0xffffffffu, candf >= 0);
+                const float gapf = fminf(t0f - lowf, upf - t0f);
+                int pickf = (candf >= 0 && gapf >= PRE_MARGIN * totf && totf < INFINITY) ? candf : -1;
+                if (whof != 0u) {
+                    const int srcf = __ffs(whof) - 1;
+                    pickf = __shfl_sync(0xffffffffu, pickf, srcf);
+                    if (pickf >= 0) {
+                        decided = true;
+                        k_new = pickf;
+                        rare = (ko < 0) ? 5 : (k_new >= K) ? 2 : 0;
+                        mg = (double)__shfl_sync(0xffffffffu, __fdividef(gapf, totf), srcf);   // a diagnostic (float accuracy)
+                    }
                 }
             }
-            const unsigned who = __ballot_sync(0xffffffffu, cand >= 0);
-            // margin of the draw: distance of the target to the nearest boundary of the drawn interval; inside the guard
-            // (relative to the total) the datum goes through the exact path.  No cumulative weight exceeds the target:
-            // utils.py:20 falls back to the last index -- a birth, the general step's business either way.
-            const double gapw = fmin(t0 - lower, upper - t0);
-            int pick = (cand >= 0) ? (cand | ((gapw >= p.guard * tot) ? 0 : 0x10000)) : 0;
-            int k_new = K, in_guard = 0, src = 0;
-            if (who != 0u) {
-                src = __ffs(who) - 1;
-                pick = __shfl_sync(0xffffffffu, pick, src);
-                k_new = pick & 0xffff;
-                in_guard = pick >> 16;
+            if (!decided) {
+                const double run = (e[0] + e[1]) + (e[2] + e[3]);
+                double incl = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 0.0;
+                const double tot = __shfl_sync(0xffffffffu, incl, 31);
+                const double t0 = u * tot;
+                int cand = -1;
+                double lower = excl, upper = excl;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (cand < 0 && 4 * lane + t <= K) {
+                        upper = lower + e[t];
+                        if (upper > t0) cand = 4 * lane + t;
+                        else lower = upper;
+                    }
+                }
+                const unsigned who = __ballot_sync(0xffffffffu, cand >= 0);
+                // margin of the draw: distance of the target to the nearest boundary of the drawn interval; inside the
+                // guard (relative to the total) the datum goes through the exact path.  No cumulative weight exceeds the
+                // target: utils.py:20 falls back to the last index -- a birth, the general step's business either way.
+                const double gapw = fmin(t0 - lower, upper - t0);
+                int pick = (cand >= 0) ? (cand | ((gapw >= p.guard * tot) ? 0 : 0x10000)) : 0;
+                int in_guard = 0;
+                if (who != 0u) {
+                    const int src = __ffs(who) - 1;
+                    pick = __shfl_sync(0xffffffffu, pick, src);
+                    k_new = pick & 0xffff;
+                    in_guard = pick >> 16;
+                    mg = __shfl_sync(0xffffffffu, margin_ratio(gapw, tot), src);
+                }
+                // anything but a stay or a plain move between two live components ends the launch (the code says why:
+                // 1 sum not finite / positive, 2 birth, 3 margin guard, 4 NaN weight, 5 unassigned datum)
+                rare = (ko < 0) ? 5 : (tot != tot) ? 4 : (!(tot > 0.0) || !(tot < INFINITY)) ? 1 : (k_new >= K) ? 2 : in_guard ? 3 : 0;
+                slow_draws += 1;
             }
-            // anything but a stay or a plain move between two live components ends the launch (the code says why:
-            // 1 sum not finite / positive, 2 birth, 3 margin guard, 4 NaN weight, 5 unassigned datum)
-            const int rare = (ko < 0) ? 5 : (tot != tot) ? 4 : (!(tot > 0.0) || !(tot < INFINITY)) ? 1 : (k_new >= K) ? 2 : in_guard ? 3 : 0;
             const bool moved = !rare && k_new != ko;
             const int stop_after = (!rare && pending_stop) ? 1 : 0;
             const unsigned long long word = (unsigned long long)(unsigned)(k_new & 0xffff) | ((unsigned long long)rare << 16) |
@@ -537,8 +597,6 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             if (lane < n_cta) st_async_u64(r_dst, word, r_bar);
             CLU_T(1);   // scan + draw
             // ---- off the critical path from here ----
-            double mg = 0.0;
-            if (who != 0u) mg = __shfl_sync(0xffffffffu, margin_ratio(gapw, tot), src);
             if (moved) {   // a component that has taken its share of rank-one changes ends the launch one step later
                 int over = 0;
 #pragma unroll
@@ -579,6 +637,7 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             __stcg(&ctl->evals, __ldcg(&ctl->evals) + steps * K);
             __stcg(&ctl->seq_data, __ldcg(&ctl->seq_data) + steps);
             __stcg(&ctl->fast_steps, __ldcg(&ctl->fast_steps) + steps);
+            __stcg(&ctl->prof[8], __ldcg(&ctl->prof[8]) + slow_draws);   // draws the single-precision scan did not decide
             atomicMin(&ctl->margin_bits, margin_bits);
         }
     }

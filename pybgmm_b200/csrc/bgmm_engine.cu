@@ -929,6 +929,8 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
             fprintf(stderr, "  cluster step timeline: draw warp wait-weights=%lld scan+draw=%lld post=%lld | comp(cta0,w0) ring=%lld eval=%lld wait=%lld upd=%lld | comp(cta1,w0) ring=%lld eval=%lld wait=%lld upd=%lld | comp(cta0,last) ring=%lld eval=%lld wait=%lld upd=%lld\n",
                     c.tprof[0][0], c.tprof[0][1], c.tprof[0][2], c.tprof[1][0], c.tprof[1][1], c.tprof[1][2], c.tprof[1][3],
                     c.tprof[2][0], c.tprof[2][1], c.tprof[2][2], c.tprof[2][3], c.tprof[3][0], c.tprof[3][1], c.tprof[3][2], c.tprof[3][3]);
+            fprintf(stderr, "  cluster step, preparation split (cta1,w0): scalars=%lld quad=%lld log=%lld exp=%lld\n", c.tprof[1][4], c.tprof[1][5],
+                    c.tprof[1][6], c.tprof[1][1]);
             static const char *tn[11] = {"stage", "A", "wait1", "finish+scan", "wait2", "draw", "wait3", "move-a", "wait4",
                                          "move-b", "wait5"};
             for (int pt = 0; pt < 4; ++pt) {
