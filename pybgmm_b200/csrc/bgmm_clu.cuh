@@ -309,20 +309,30 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
         double tw = fetch_win(wc), tw2 = 0.0;
         int pend = 0;   // steps until the requested window tw2 replaces tw (the load has two steps to land)
         const double hh0 = 0.5 * (double)(p.v0 + 1);   // H(n) = (nu + D) / 2 = (v0 + 1 + n) / 2
-        // everything in a record that depends on the count alone (bgmm_fast.cuh NT_*), from the window; nn may differ
-        // from lane to lane
+        // everything in a record that depends on the count alone (bgmm_fast.cuh NT_*) for the counts n - 1, n, n + 1,
+        // out of the window whenever n changes: cnw[i] = CN(n - 2 + i), rkw[i] = 1 / kappa(n - 2 + i)
         struct NS { double cn_n, cn_m, g, beta, hh; };
-        auto nscal = [&](double nn) -> NS {
-            const int r = (int)((long long)nn - (wc - 8));   // row of nn inside the window
+        double cnw[4], rkw[5];
+        auto load_counts = [&]() {
+            const int r = (int)((long long)n - (wc - 8));   // row of n inside the window
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cnw[i] = __shfl_sync(0xffffffffu, tw, (2 * (r - 2 + i)) & 31);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) rkw[i] = __shfl_sync(0xffffffffu, tw, (2 * (r - 2 + i) + 1) & 31);
+        };
+        // count nn = n + dn, dn in {-1, 0, 1}: G = kappa / (kappa + 1) = 1 - 1 / kappa(nn + 1), BETA = kappa / (kappa - 1)
+        // = 1 + 1 / kappa(nn - 1)
+        auto ns_of = [&](int dn) -> NS {
             NS o;
-            o.cn_n = __shfl_sync(0xffffffffu, tw, (2 * r) & 31);
-            o.cn_m = __shfl_sync(0xffffffffu, tw, (2 * r - 2) & 31);
-            o.g = 1.0 - __shfl_sync(0xffffffffu, tw, (2 * r + 3) & 31);      // kappa / (kappa + 1) = 1 - 1 / kappa(n + 1)
-            o.beta = 1.0 + __shfl_sync(0xffffffffu, tw, (2 * r - 1) & 31);   // kappa / (kappa - 1) = 1 + 1 / kappa(n - 1)
-            o.hh = hh0 + 0.5 * nn;
+            o.cn_n = dn < 0 ? cnw[1] : dn == 0 ? cnw[2] : cnw[3];
+            o.cn_m = dn < 0 ? cnw[0] : dn == 0 ? cnw[1] : cnw[2];
+            o.g = 1.0 - (dn < 0 ? rkw[2] : dn == 0 ? rkw[3] : rkw[4]);
+            o.beta = 1.0 + (dn < 0 ? rkw[0] : dn == 0 ? rkw[1] : rkw[2]);
+            o.hh = hh0 + 0.5 * (n + (double)dn);
             return o;
         };
-        NS ns_st = nscal(n);
+        load_counts();
+        NS ns_st = ns_of(0);
         const uint32_t e_dst = map_to_cta(&S.ebuf[k], 0), e_bar = map_to_cta(&S.ebar, 0);
         const bool armer = (warp == 0);
         double *vx = S.vx[warp];
@@ -389,10 +399,9 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             const double gam = side ? -(beta * rd) : beta * rd;
             const double n2 = alt_ok ? n + (side ? 1.0 : -1.0) : n;
             const double n_sel = (sel == 1) ? n2 : n;
-            const NS nsx = nscal(n_sel);
-            const int r2 = (int)((long long)n2 - (wc - 8));
-            const double rkk = __shfl_sync(0xffffffffu, tw, (2 * r2 + 1) & 31);
-            const double rk = side ? -rkk : rkk;   // m' = m -+ d_s / kappa(n2), d_s = m - x_s
+            const int dn = alt_ok ? (side ? 1 : -1) : 0;
+            const NS nsx = ns_of((sel == 1) ? dn : 0);
+            const double rk = side ? -rkw[3] : rkw[1];   // m' = m -+ d_s / kappa(n2), d_s = m - x_s
             CLU_T(4);   // scalars of the other outcome
             double e_u = 0.0, e_a = 0.0, q_u = 0.0, q_a = 0.0, sg = 0.0, w = 0.0, al_lds = lds;
             {
@@ -452,7 +461,8 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
                 ma = fma(ma - S.xr[slot][a], rk, ma);
                 n = n2;
                 lds = al_lds;
-                ns_st = nscal(n);
+                load_counts();
+                ns_st = ns_of(0);
                 const long long n_now = (long long)n;
                 if (pend == 0 && (n_now - wc >= 3 || wc - n_now >= 3)) { wc2 = n_now; tw2 = fetch_win(n_now); pend = 2; }
                 cur_v = fma(fma(gam, sg, rk), cur_v, w);   // B' d' = B d + (rk + gam sigma) v
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
         long long moves = 0, steps = 0, n_log = 0, pos = j1, slow_draws = 0;
         unsigned long long margin_bits;
         { const double one = 1.0; margin_bits = (unsigned long long)__double_as_longlong(one); }
-        int why = 0;
+        int why = 0, refreshed = 0;
         bool stopped = false, pending_stop = false;
         SpinWatch wd;
         CLU_TDECL;
@@ -624,7 +634,7 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
                 n_log += 1;
                 moves += 1;
             }
-            if (stop_after) { pos = j + 1; break; }
+            if (stop_after) { pos = j + 1; refreshed = 1; break; }
         }
         CLU_TFLUSH(0);
         if (lane == 0) {
@@ -637,6 +647,7 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             __stcg(&ctl->evals, __ldcg(&ctl->evals) + steps * K);
             __stcg(&ctl->seq_data, __ldcg(&ctl->seq_data) + steps);
             __stcg(&ctl->fast_steps, __ldcg(&ctl->fast_steps) + steps);
+            __stcg(&ctl->refreshes, __ldcg(&ctl->refreshes) + refreshed);   // the launch ended for a rebuild of the records
             __stcg(&ctl->prof[8], __ldcg(&ctl->prof[8]) + slow_draws);   // draws the single-precision scan did not decide
             atomicMin(&ctl->margin_bits, margin_bits);
         }

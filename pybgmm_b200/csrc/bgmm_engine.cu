@@ -811,6 +811,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         events_on = true;
         long long pos = 0;
         bool to_generic = false, to_fast = false;
+        long long handbacks = 0;
         long long span = use_clu ? 8192 : big::BIG_SPAN;   // a short first span: the regime shows early
         while (pos < h->N) {
             p.start_pos = pos;
@@ -832,6 +833,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
             c.win = 0;
             if (c.error == big::E_RARE) {
                 // the generic engine's (Cholesky) records follow from the statistics; its step resolves the datum
+                handbacks += 1;
                 c.error = 0;
                 CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
                 if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
@@ -846,8 +848,12 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
                 break;
             }
             if (use_clu && h->engine == 0 && walked >= 4096 && pos < h->N &&
-                (double)walked / (double)(moved + 1) >= 2.0 * h->clu_gap) {
+                (double)walked / (double)(moved + 1) >= 1.25 * h->clu_gap) {
                 to_fast = true;   // sparse movers: speculative windows are the better engine for the rest of the sweep
+                break;
+            }
+            if (use_clu && h->engine == 0 && handbacks >= 16 && handbacks * 1500 > pos && pos < h->N) {
+                to_fast = true;   // births / deaths every few hundred data: the resident engine resolves them in-kernel
                 break;
             }
         }

@@ -189,11 +189,14 @@ def test_resident_capacity_overflow_hands_over_to_generic(gpu_lib):
     _assert_state_equal(orc, ch)
 
 
-def test_long_chain_drift_control(gpu_lib):
-    """Many rank-one record updates per component (records are rebuilt from the bit-exact statistics every
-    REFRESH_EVERY updates): the chain still follows the oracle and the statistics stay bit-identical."""
+@pytest.mark.parametrize("engine", ["sequential", "cluster"])
+def test_long_chain_drift_control(gpu_lib, engine):
+    """Many rank-one record updates per component: the resident engine rebuilds a record from the bit-exact statistics
+    every REFRESH_EVERY updates, the cluster step engine ends its launch when a component has taken REFRESH_CAP of them
+    (records are rebuilt at every launch); the chain still follows the oracle and the statistics stay bit-identical."""
     N, D, K_true = 6000, 8, 3
     X, orc, ch = _pair(gpu_lib, N, D, K_true, "full", K_init=3, K_max=32)
+    ch.set_engine(engine)
     rng = np.random.RandomState(11)
     refreshes = 0
     for s in range(3):
