@@ -182,7 +182,7 @@ template <int DP> __device__ __forceinline__ double bsym(const double *__restric
 // the sweep kernel: one cluster per chain
 // ---------------------------------------------------------------------------------------------
 template <int DP>
-__global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const double *__restrict__ rec_in, long long pos_limit,
+__global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, double *__restrict__ rec_in, long long pos_limit,
                                                     int4 *__restrict__ mlog) {
     using L = BL<DP>;
     constexpr int C = L::C, NL = L::NL, R = L::R;
@@ -430,6 +430,12 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
     // ---- epilogue ----
     __syncthreads();
     for (int l = tid; l < Lc; l += TB) __stcg(p.counts + (l * C + c), (long long)s.rec[(size_t)l * R + L::SC + F_N]);
+    // the records as they are now, for the next launch (the host rebuilds them from the statistics every BIG_SPAN data or
+    // after the general step changed anything)
+    for (int l = 0; l < Lc; ++l) {
+        double *dst = rec_in + (size_t)(l * C + c) * R;
+        for (int e = tid; e < R; e += TB) __stcg(dst + e, s.rec[(size_t)l * R + e]);
+    }
     if (c == 0 && tid == 0) {
         __stcg(&ctl->pos, pos);
         __stcg(&ctl->error, stop ? E_RARE : 0);
@@ -442,6 +448,136 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, const do
         atomicMin(&ctl->margin_bits, sh.margin_bits);
     }
     cluster_sync_all();   // no CTA exits while another may still store into its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sparse movers: which of the data at scan positions [pos0, pos1) provably STAY, given the records as they are now?
+// Data-parallel over the whole GPU: a CTA takes a tile of WT consecutive positions; for every component the full
+// symmetric B (DP x DP) is staged in shared memory once per tile and Y = B (m - X_tile) is a register-blocked product
+// (thread = RPT rows x one datum, B broadcast across the warp: the FP64 pipe is the limit, not shared memory); then
+// the weights, the cumulative sums in the reference's order and the draw (crpmm.py:70-78, utils.py:7-20).  A datum whose
+// draw is its own component with a margin of at least Params::guard stays whatever arithmetic is used; the first
+// position that does not is the atomicMin target Ctl::first -- the host hands the chain over to k_big_sweep there,
+// and everything behind it is evaluated again later (its weights may change with that datum's move).
+// Dynamic shared memory: big_window_smem<DP>().
+// ---------------------------------------------------------------------------------------------
+constexpr int WT = 32;   // positions per tile
+
+template <int DP> constexpr size_t big_window_smem() {
+    return sizeof(double) * ((size_t)DP * DP + (size_t)DP * WT + (size_t)KCH * WT + 8 * WT + DP + NSC + fm::TAB_LEN);
+}
+
+template <int DP>
+__global__ void __launch_bounds__(256) k_big_window(const Params p, const double *__restrict__ rec_in, int K, long long pos0,
+                                                    long long pos1) {
+    using L = BL<DP>;
+    constexpr int NL = L::NL, R = L::R, RPT = DP / 8;
+    extern __shared__ __align__(16) double wsm[];
+    double *Bt = wsm;                       // Bt[b * DP + a] = B[a][b]
+    double *Xs = Bt + DP * DP;              // Xs[b * WT + t]
+    double *E = Xs + DP * WT;               // E[k * WT + t]
+    double *qp = E + KCH * WT;              // partial quadratic forms: qp[g * WT + t]
+    double *mk = qp + 8 * WT;               // mean (DP) and scalars (NSC) of the component being evaluated
+    double *fmt = mk + DP + NSC;
+    __shared__ long long js[WT];
+    __shared__ int kos[WT];
+    __shared__ double us[WT], lps[WT];
+    __shared__ int stop_s;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    Ctl *ctl = p.ctl;
+    for (int e = tid; e < fm::TAB_LEN; e += 256) fmt[e] = __ldg(p.fmtab + e);
+    const long long n_tiles = (pos1 - pos0 + WT - 1) / WT;
+    unsigned long long margin_bits;
+    { const double one = 1.0; margin_bits = (unsigned long long)__double_as_longlong(one); }
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long jb = pos0 + tile * WT;
+        __syncthreads();
+        if (tid == 0) stop_s = (jb > __ldcg(&ctl->first)) ? 1 : 0;   // an earlier position already ends the window
+        __syncthreads();
+        if (stop_s) break;
+        if (tid < WT) {
+            const long long j = jb + tid;
+            const bool valid = j < pos1;
+            long long i = 0;
+            if (valid) i = p.order ? p.order[j] : j;
+            js[tid] = valid ? i : -1;
+            int ko = -1;
+            if (valid) { const int uid = __ldcg(p.z_uid + i); ko = uid >= 0 ? __ldcg(p.slot_of_uid + uid) : -1; }
+            kos[tid] = ko;
+            us[tid] = valid ? p.u[j] : 0.0;
+            lps[tid] = valid ? p.log_prior[i] : 0.0;
+        }
+        __syncthreads();
+        for (int e = tid; e < DP * WT; e += 256) {
+            const int t = e / DP, b = e % DP;
+            const long long i = js[t];
+            Xs[b * WT + t] = i >= 0 ? p.X[(size_t)i * DP + b] : 0.0;
+        }
+        for (int k = 0; k < K; ++k) {
+            __syncthreads();
+            const double *rk = rec_in + (size_t)k * R;
+            for (int e = tid; e < L::PP; e += 256) {   // the packed triangle (lane-interleaved rows, see pidx) -> full matrix
+                const int ln = e % NL, j = e / NL;
+                int a, b;
+                if (j <= ln) { a = ln; b = j; } else { a = DP - 1 - ln; b = j - ln - 1; }
+                const double v = __ldcg(rk + e);
+                Bt[b * DP + a] = v;
+                Bt[a * DP + b] = v;
+            }
+            for (int e = tid; e < DP + NSC; e += 256) mk[e] = __ldcg(rk + L::MU + e);
+            __syncthreads();
+            double y[RPT];
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) y[r] = 0.0;
+#pragma unroll 4
+            for (int b = 0; b < DP; ++b) {
+                const double d = mk[b] - Xs[b * WT + tx];
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) y[r] = fma(Bt[b * DP + ty * RPT + r], d, y[r]);
+            }
+            double part = 0.0;
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) part = fma(mk[ty * RPT + r] - Xs[(ty * RPT + r) * WT + tx], y[r], part);
+            qp[ty * WT + tx] = part;
+            __syncthreads();
+            if (ty == 0) {
+                double q = 0.0;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) q += qp[g * WT + tx];
+                const double *sc = mk + DP;
+                const int own = (k == kos[tx]) ? 1 : 0;
+                double e = fast::f_finish_weight<1>(sc, q, own, p.log_alpha + lps[tx], fmt);
+                if (own && sc[F_N] == 1.0) e = NAN;   // the datum is its component's last member: not a plain stay
+                E[k * WT + tx] = e;
+            }
+        }
+        __syncthreads();
+        if (tid < WT && js[tid] >= 0) {
+            const int ko = kos[tid];
+            double tot = 0.0;
+            for (int k = 0; k < K; ++k) tot += E[k * WT + tid];
+            tot += 1.0;   // the new component: exp(reference - reference)
+            const double t0 = us[tid] * tot;
+            double lower = 0.0, upper = 0.0;
+            int kd = K;
+            for (int k = 0; k < K; ++k) {
+                upper = lower + E[k * WT + tid];
+                if (upper > t0) { kd = k; break; }
+                lower = upper;
+            }
+            bool stays = false;
+            if (kd == ko && ko >= 0 && tot > 0.0 && tot < INFINITY) {
+                const double gapw = fmin(t0 - lower, upper - t0);
+                if (gapw >= p.guard * tot) {
+                    stays = true;
+                    const unsigned long long mb = (unsigned long long)__double_as_longlong(margin_ratio(gapw, tot));
+                    if (mb < margin_bits) margin_bits = mb;
+                }
+            }
+            if (!stays) atomicMin(&ctl->first, jb + tid);
+        }
+    }
+    if (tid < WT) atomicMin(&ctl->margin_bits, margin_bits);
 }
 
 // ---------------------------------------------------------------------------------------------

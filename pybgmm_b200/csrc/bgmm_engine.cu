@@ -805,6 +805,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
                          (h->engine == 6 || (h->engine == 0 && h->last_gap < h->clu_gap));
     bool big_done = false;
     bool events_on = false;
+    long long x_evals = 0, x_steps = 0, x_windows = 0, x_wasted = 0;   // data certified by k_big_window (host-side counts)
     long long resume_at = 0;   // the resident engine starts here when the step engine handed over
     if (use_big || use_clu) {
         CU(cudaEventRecord(h->ev2, st));
@@ -812,11 +813,43 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         long long pos = 0;
         bool to_generic = false, to_fast = false;
         long long handbacks = 0;
-        long long span = use_clu ? 8192 : big::BIG_SPAN;   // a short first span: the regime shows early
+        long long span = (use_clu || h->engine == 0) ? 8192 : big::BIG_SPAN;   // a short first span: the regime shows early
+        // D = 32 / 64, sparse movers: a data-parallel window kernel certifies the data that stay (k_big_window) and the
+        // cluster steps only through the neighbourhood of the first datum that does not
+        const double BIG_WIN_GAP = 16.0;
+        const long long BIG_STEP_SPAN = 8;
+        double gap_est = h->last_gap;
+        bool win_mode = use_big && h->engine == 0 && gap_est >= BIG_WIN_GAP;
+        long long wlen = 4096, since_prep = 0;
+        bool need_prep = true;
         while (pos < h->N) {
             p.start_pos = pos;
-            if (int rc = use_clu ? h->ops->clu_prep(h, p, c.K) : h->ops->big_prep(h, p, c.K)) return rc;
-            if (int rc = check_dev_err(h, "sweep (record set-up)")) return rc;
+            if (need_prep || use_clu || since_prep >= big::BIG_SPAN) {
+                if (int rc = use_clu ? h->ops->clu_prep(h, p, c.K) : h->ops->big_prep(h, p, c.K)) return rc;
+                if (int rc = check_dev_err(h, "sweep (record set-up)")) return rc;
+                need_prep = false;
+                since_prep = 0;
+            }
+            long long stays = 0;
+            if (win_mode) {
+                const long long wlim = std::min<long long>(h->N, pos + wlen);
+                const long long inf = POS_INF;
+                CU(cudaMemcpyAsync((char *)h->d_ctl + offsetof(Ctl, first), &inf, sizeof(inf), cudaMemcpyHostToDevice, st));
+                if (int rc = h->ops->big_window(h, p, c.K, pos, wlim)) return rc;
+                CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                const long long f = std::min<long long>(c.first, wlim);
+                stays = f - pos;
+                x_evals += stays * c.K; x_steps += stays; x_windows += 1; x_wasted += wlim - f;
+                since_prep += stays;
+                if (getenv("BGMM_WPROF"))
+                    fprintf(stderr, "  window from %lld to %lld: first non-stay %lld\n", pos, wlim, f);
+                pos = f;
+                if (f == wlim) { wlen = std::min<long long>(wlen * 2, 1LL << 20); continue; }
+                wlen = std::max<long long>(1024, std::min<long long>(1LL << 20, (long long)(4.0 * gap_est)));
+                p.start_pos = pos;
+                span = BIG_STEP_SPAN;
+            }
             const long long lim = std::min<long long>(h->N, pos + span);
             const long long moves_before = c.moves;
             if (int rc = use_clu ? h->ops->clu_sweep(h, p, lim) : h->ops->big_sweep(h, p, lim)) return rc;
@@ -828,6 +861,12 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
             const long long walked = c.pos - pos, moved = c.moves - moves_before;
             pos = c.pos;
             span = big::BIG_SPAN;
+            since_prep += walked;
+            if (use_big && h->engine == 0) {
+                const double g_now = (double)(stays + walked) / (double)(moved + 1);
+                gap_est = win_mode ? 0.75 * gap_est + 0.25 * g_now : g_now;
+                win_mode = win_mode ? gap_est >= 0.5 * BIG_WIN_GAP : (walked >= 1024 && gap_est >= BIG_WIN_GAP);
+            }
             // the bit-exact statistics follow from the launch's move log (one CTA per component, chain order)
             if (int rc = h->ops->big_replay(h, p, c.K, c.win)) return rc;
             c.win = 0;
@@ -838,6 +877,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
                 CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
                 if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
                 h->launches += 1;
+                need_prep = true;
                 if (int rc = h->ops->resolve_one(h, p, pos)) return rc;
                 CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
                 CU(cudaStreamSynchronize(st));
@@ -918,6 +958,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
     CU(cudaEventRecord(h->ev1, st));
     CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    c.evals += x_evals; c.seq_data += x_steps; c.fast_steps += x_steps; c.windows += x_windows; c.wasted += x_wasted;
     float ms = 0.f, ms_k = 0.f;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     CU(cudaEventElapsedTime(&ms_k, h->ev2, h->ev3));
