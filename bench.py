@@ -132,14 +132,34 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_profile(workload, regime):
-    """Per-launch figures of the sweep kernel from the committed `ncu --set full` capture of `regime` (cold / window /
-    converged), profiles/ncu_traffic.json: DRAM bytes, FP64 pipe %, issue-active %.  None when no capture exists."""
+def ncu_profile(workload, regime, N):
+    """Per-sweep figures of the kernel that runs `regime` (cold / window / converged) from the committed `ncu --set full`
+    capture, profiles/ncu_traffic.json: DRAM bytes, FP64 pipe %, issue-active %.  A capture taken on one launch that
+    covers part of a sweep (the cluster step engine: a launch is a span of the scan) carries `dram_bytes_per_datum`;
+    the sweep's traffic is that times N.  None when no capture exists."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            return json.load(fh).get(workload, {}).get(regime)
+            prof = json.load(fh).get(workload, {}).get(regime)
     except Exception:
         return None
+    if prof and "dram_bytes" not in prof and "dram_bytes_per_datum" in prof:
+        prof = dict(prof, dram_bytes=prof["dram_bytes_per_datum"] * N)
+    return prof
+
+
+def kernel_of(cov, D, regime):
+    """The kernel a timed sweep of this regime spends its time in."""
+    DP = next(d for d in (1, 2, 4, 8, 16, 32, 64) if d >= D)
+    if cov == "full" and DP <= 16:
+        if regime == "cold":
+            return ("k_clu_sweep<%d>: thread-block cluster of 16 CTAs, one warp per component, weights and draws over DSMEM; "
+                    "a sweep is a few dozen launches (spans of the scan)" % DP)
+        return "k_fast_sweep<%d> (148 replicated CTAs, speculative windows; one launch = one sweep)" % DP
+    if cov == "full" and DP in (32, 64):
+        if regime == "cold":
+            return "k_big_sweep<%d> (thread-block cluster, records over DSMEM; a sweep is a few launches)" % DP
+        return "k_big_window<%d> (data-parallel stay test) + k_big_sweep<%d> around the movers" % (DP, DP)
+    return "k_sweep (generic engine)"
 
 
 def regime_of(moves, N):
@@ -495,7 +515,7 @@ def run_ours(a):
         r["evals_per_s"] = r["evals"] / (r["ms"] * 1e-3) if r["ms"] > 0 else None
         r["us_per_mover"] = 1e3 * r["ms"] / r["moves"] if r["moves"] else None
     dominant = max(regimes, key=lambda k: regimes[k]["ms"])
-    prof = ncu_profile(wl, dominant) or {}
+    prof = ncu_profile(wl, dominant, N) or {}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -519,14 +539,12 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": prof.get("dram_bytes"), "traffic_regime": dominant if prof else None,
                      "peak_source": peak_src,
-                     "kernel": ("k_fast_sweep<%d> (one launch = one sweep)" % D if (cov == "full" and D <= 16) else
-                                "k_big_sweep<%d> (thread-block cluster; a sweep is a few launches)" % D
-                                if (cov == "full" and D in (32, 64)) else "k_sweep"),
+                     "kernel": kernel_of(cov, D, dominant),
                      "algorithmic_bytes_per_eval": b_eval, "algorithmic_bytes_per_datum": b_datum,
-                     "kernel_ms_per_launch": kernel_ms / K,
-                     "true_bound": "latency of the sequential dependency: every datum that moves is one serial step "
-                                   "(cold regime) or one window round (window regime); HBM and the FP64 pipe are "
-                                   "both far from saturated",
+                     "kernel_ms_per_launch": kernel_ms / K, "launches_per_step": launches / K,
+                     "true_bound": "latency of the sequential dependency: every datum is one serial step of the cluster "
+                                   "(cold regime: two DSMEM hops + one scan of the K + 1 weights) or every mover one "
+                                   "window round (window regime); HBM and the FP64 pipe are both far from saturated",
                      "fp64_tflops": evals * 2 * flops_eval / (kernel_ms * 1e-3) / 1e12,
                      "ncu": prof or None,
                      "note": "secondary figure: ALGORITHMIC bytes per SURVEY.md 8(d) (one sufficient-statistic record "
