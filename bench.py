@@ -566,12 +566,12 @@ def run_ours(a):
         line["multi_chain"] = multi
     if world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(wl)
+    if world > 1:
+        dist.destroy_process_group()      # while stdout still points at stderr: NCCL logs its teardown at NCCL_DEBUG=INFO
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def run_multi_chain(a, _lib, torch, dev, X, z0_first, prior, K_max, cov, power, N, K):
