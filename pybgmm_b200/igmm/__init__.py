@@ -4,5 +4,6 @@ from .crpmm import CRPMM
 from .pcrpmm import PCRPMM
 from .adapcrpmm import ADAPCRPMM
 from .cscrpmm import CSCRPMM
+from .subcrpmm import SubCRPMM
 
-__all__ = ["IGMM", "CRPMM", "PCRPMM", "ADAPCRPMM", "CSCRPMM"]
+__all__ = ["IGMM", "CRPMM", "PCRPMM", "ADAPCRPMM", "CSCRPMM", "SubCRPMM"]

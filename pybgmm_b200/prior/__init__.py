@@ -1,3 +1,4 @@
 from .niw import NIW
+from .betabern import BetaBern
 
-__all__ = ["NIW"]
+__all__ = ["NIW", "BetaBern"]
