@@ -132,6 +132,9 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+FP64_PEAK_TFLOPS = 40.0   # nominal vector FP64 of one B200 (no measured figure in MEASURED_PEAKS.json)
+
+
 def ncu_profile(workload, regime, N):
     """Per-sweep figures of the kernel that runs `regime` (cold / window / converged) from the committed `ncu --set full`
     capture, profiles/ncu_traffic.json: DRAM bytes, FP64 pipe %, issue-active %.  A capture taken on one launch that
@@ -559,6 +562,16 @@ def run_ours(a):
                    "wasted": [int(st.wasted) for st in stats], "min_margin": min(st.min_margin for st in stats),
                    "guard_hits": int(sum(st.guard_hits for st in stats) + sweep0.guard_hits)},
     }
+    if achieved / peak > 1.0:
+        # the records are reused from shared memory (k_big_window stages B once per 32 data): algorithmic bytes over time
+        # exceed the HBM peak and say nothing about HBM.  The kernel is an FP64 product: report the compute fraction,
+        # explicitly labelled (vector FP64 FMAs, not tensor cores; no measured FP64 peak in MEASURED_PEAKS.json)
+        rf = line["roofline"]
+        rf["hbm_algorithmic"] = {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                 "note": "above 1: not evidence of HBM utilisation"}
+        rf.update({"bound": "tensor", "achieved": rf["fp64_tflops"], "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                   "frac": rf["fp64_tflops"] / FP64_PEAK_TFLOPS, "pipe": "fp64 vector FMA (no tensor cores on this path)",
+                   "peak_source": "nominal B200 FP64 peak %.0f TFLOP/s (MEASURED_PEAKS.json holds no FP64 figure)" % FP64_PEAK_TFLOPS})
     if gather_ms is not None:
         line["gather_assignments_ms"] = {"first_call": gather_ms[0], "steady": gather_ms[1]}
         line["per_rank"] = per_rank
