@@ -585,6 +585,8 @@ def run_ours(a):
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
+    if saved_stdout is not None:
+        os.dup2(2, 1)      # whatever a library still prints while the process exits (NCCL at NCCL_DEBUG=INFO) is not stdout's
 
 
 def run_multi_chain(a, _lib, torch, dev, X, z0_first, prior, K_max, cov, power, N, K):

@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, double *
 constexpr int WT = 32;   // positions per tile
 
 template <int DP> constexpr size_t big_window_smem() {
-    return sizeof(double) * ((size_t)DP * DP + (size_t)DP * WT + (size_t)KCH * WT + 8 * WT + DP + NSC + fm::TAB_LEN);
+    return sizeof(double) * ((size_t)DP * (DP + 2) + (size_t)DP * WT + (size_t)KCH * WT + 8 * WT + DP + NSC + fm::TAB_LEN);
 }
 
 template <int DP>
@@ -472,9 +472,11 @@ __global__ void __launch_bounds__(256) k_big_window(const Params p, const double
                                                     long long pos1) {
     using L = BL<DP>;
     constexpr int NL = L::NL, R = L::R, RPT = DP / 8;
+    constexpr int BS = DP + 2;              // row stride of the staged matrix: the transposed stores of the staging spread
+                                            // over the banks (stride DP: 32-way conflicts), rows stay 16-byte aligned
     extern __shared__ __align__(16) double wsm[];
-    double *Bt = wsm;                       // Bt[b * DP + a] = B[a][b]
-    double *Xs = Bt + DP * DP;              // Xs[b * WT + t]
+    double *Bt = wsm;                       // Bt[b * BS + a] = B[a][b]
+    double *Xs = Bt + DP * BS;              // Xs[b * WT + t]
     double *E = Xs + DP * WT;               // E[k * WT + t]
     double *qp = E + KCH * WT;              // partial quadratic forms: qp[g * WT + t]
     double *mk = qp + 8 * WT;               // mean (DP) and scalars (NSC) of the component being evaluated
@@ -515,14 +517,19 @@ __global__ void __launch_bounds__(256) k_big_window(const Params p, const double
         }
         for (int k = 0; k < K; ++k) {
             __syncthreads();
+            if ((k & 7) == 7) {   // an earlier position ended the window meanwhile: this tile's answer is not needed
+                if (tid == 0) stop_s = (jb > __ldcg(&ctl->first)) ? 1 : 0;
+                __syncthreads();
+                if (stop_s) break;
+            }
             const double *rk = rec_in + (size_t)k * R;
             for (int e = tid; e < L::PP; e += 256) {   // the packed triangle (lane-interleaved rows, see pidx) -> full matrix
                 const int ln = e % NL, j = e / NL;
                 int a, b;
                 if (j <= ln) { a = ln; b = j; } else { a = DP - 1 - ln; b = j - ln - 1; }
                 const double v = __ldcg(rk + e);
-                Bt[b * DP + a] = v;
-                Bt[a * DP + b] = v;
+                Bt[b * BS + a] = v;
+                Bt[a * BS + b] = v;
             }
             for (int e = tid; e < DP + NSC; e += 256) mk[e] = __ldcg(rk + L::MU + e);
             __syncthreads();
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(256) k_big_window(const Params p, const double
             for (int b = 0; b < DP; ++b) {
                 const double d = mk[b] - Xs[b * WT + tx];
 #pragma unroll
-                for (int r = 0; r < RPT; ++r) y[r] = fma(Bt[b * DP + ty * RPT + r], d, y[r]);
+                for (int r = 0; r < RPT; ++r) y[r] = fma(Bt[b * BS + ty * RPT + r], d, y[r]);
             }
             double part = 0.0;
 #pragma unroll
@@ -552,6 +559,7 @@ __global__ void __launch_bounds__(256) k_big_window(const Params p, const double
             }
         }
         __syncthreads();
+        if (stop_s) break;
         if (tid < WT && js[tid] >= 0) {
             const int ko = kos[tid];
             double tot = 0.0;

@@ -846,7 +846,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
                     fprintf(stderr, "  window from %lld to %lld: first non-stay %lld\n", pos, wlim, f);
                 pos = f;
                 if (f == wlim) { wlen = std::min<long long>(wlen * 2, 1LL << 20); continue; }
-                wlen = std::max<long long>(1024, std::min<long long>(1LL << 20, (long long)(4.0 * gap_est)));
+                wlen = std::max<long long>(4096, std::min<long long>(1LL << 20, (long long)(8.0 * gap_est)));   // one wave of tiles costs the same up to ~9 k positions
                 p.start_pos = pos;
                 span = BIG_STEP_SPAN;
             }
