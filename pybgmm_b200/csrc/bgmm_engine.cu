@@ -817,7 +817,7 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         // D = 32 / 64, sparse movers: a data-parallel window kernel certifies the data that stay (k_big_window) and the
         // cluster steps only through the neighbourhood of the first datum that does not
         const double BIG_WIN_GAP = 16.0;
-        const long long BIG_STEP_SPAN = 8;
+        const long long BIG_STEP_SPAN = 2;
         double gap_est = h->last_gap;
         bool win_mode = use_big && h->engine == 0 && gap_est >= BIG_WIN_GAP;
         long long wlen = 4096, since_prep = 0;
@@ -866,6 +866,9 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
                 const double g_now = (double)(stays + walked) / (double)(moved + 1);
                 gap_est = win_mode ? 0.75 * gap_est + 0.25 * g_now : g_now;
                 win_mode = win_mode ? gap_est >= 0.5 * BIG_WIN_GAP : (walked >= 1024 && gap_est >= BIG_WIN_GAP);
+                // between the regimes the cluster walks short spans, so that a dense patch of movers inside a sparse sweep
+                // does not cost a whole BIG_SPAN of 4 us steps before the windows are tried again
+                if (!win_mode && gap_est >= 4.0) span = 2048;
             }
             // the bit-exact statistics follow from the launch's move log (one CTA per component, chain order)
             if (int rc = h->ops->big_replay(h, p, c.K, c.win)) return rc;
