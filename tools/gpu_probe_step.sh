@@ -1,4 +1,5 @@
 #!/bin/bash
+# cluster step engine: parity tests, per-sweep probe at C3 / C2, in-kernel timeline (profile build: tools/build_prof.sh)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_clu.py -x -q --timeout 300 --timeout-method=thread > gpurun_out/pytest_clu.log 2>&1
 echo "pytest rc=$?"; tail -15 gpurun_out/pytest_clu.log | cut -c1-300
