@@ -72,3 +72,58 @@ def test_adaptive_policy_uses_the_step_engine_then_the_windows(gpu_lib):
     np.testing.assert_array_equal(out[0][2], out[1][2])
     np.testing.assert_array_equal(out[0][3], out[1][3])
     assert out[0][0][0][5] == 0 and out[0][0][-1][5] > 0, out[0][0]   # first sweep: no windows; last sweep: windows
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 65, 257])
+def test_cluster_step_engine_ragged_sizes(gpu_lib, N):
+    """Chains shorter than / not a multiple of the producer's ring (32 data per half): every datum is still visited once,
+    in order, and the chain is the oracle's."""
+    D = 3
+    X, _ = make_data(max(N, 4), D, 2, 9)
+    X = np.ascontiguousarray(X[:N])
+    m_0, k_0, v_0, S_0 = make_prior(D)
+    rng = np.random.RandomState(N)
+    z0 = np.unique(rng.randint(0, 3, N), return_inverse=True)[1].astype(np.int64)
+    orc = O.Oracle(X, m_0, k_0, v_0, S_0, K_max=max(8, N))
+    orc.set_assignments(z0)
+    ch = gpu_lib.Chain(X, m_0, k_0, v_0, S_0, max(8, N))
+    ch.set_engine("cluster")
+    ch.set_assignments(z0)
+    for s in range(3):
+        u = rng.random_sample(N)
+        so = orc.sweep(u, 1.0)
+        sg = ch.sweep(1.0, 1.0, None, u)
+        assert (sg.K, sg.moves, sg.births, sg.deaths, sg.evals) == (so.K_end, so.moves, so.births, so.deaths, so.evals), s
+        np.testing.assert_array_equal(ch.assignments(), orc.assignments)
+    st = ch.get_state(inv_covar=False)
+    np.testing.assert_array_equal(st["m_num"], orc.m_N_numerators)
+    np.testing.assert_array_equal(st["S_part"], orc.S_N_partials)
+
+
+def test_cluster_step_engine_with_many_births_and_deaths(gpu_lib):
+    """A large alpha opens components all the time and most die again: every one of them is a hand-back to the general
+    step (and past a rate of one per few hundred data the adaptive policy leaves the cluster engine for the resident one,
+    which resolves them in-kernel); both policies walk the oracle's chain."""
+    N, D = 4000, 2
+    X, _ = make_data(N, D, 5, 6)
+    m_0, k_0, v_0, S_0 = make_prior(D)
+    for engine in ("cluster", "adaptive"):
+        rng = np.random.RandomState(31)
+        z0 = np.unique(rng.randint(0, 6, N), return_inverse=True)[1].astype(np.int64)
+        orc = O.Oracle(X, m_0, k_0, v_0, S_0, K_max=400)
+        orc.set_assignments(z0)
+        ch = gpu_lib.Chain(X, m_0, k_0, v_0, S_0, 400)
+        ch.set_engine(engine)
+        ch.set_assignments(z0)
+        births = 0
+        for s in range(3):
+            u = rng.random_sample(N)
+            so = orc.sweep(u, 60.0)
+            sg = ch.sweep(60.0, 1.0, None, u)
+            births += so.births
+            assert (sg.K, sg.moves, sg.births, sg.deaths, sg.evals) == (so.K_end, so.moves, so.births, so.deaths, so.evals), (engine, s)
+            np.testing.assert_array_equal(ch.assignments(), orc.assignments)
+        assert births > 50
+        st = ch.get_state(inv_covar=False)
+        np.testing.assert_array_equal(st["S_part"], orc.S_N_partials)
+        ch.close()
