@@ -54,13 +54,14 @@ typedef struct {
     double min_margin;  /* min distance of a uniform to the CDF boundary it was compared with         */
     double device_ms;   /* CUDA-event time of the sweep kernel(s), summed                             */
     int64_t explicit_evals; /* own-component weights rebuilt exactly from the statistics (engine diagnostic)  */
-    int64_t refreshes;      /* records rebuilt from the statistics for drift control (engine diagnostic)      */
+    int64_t refreshes;      /* records rebuilt from the statistics for drift control, incl. cluster launches ended for it  */
     int64_t generic_from;   /* scan position the generic engine took over at, or -1 (engine diagnostic)       */
     int64_t phase_cycles[16]; /* SM cycles CTA 0 spent per engine phase in the last sweep (engine diagnostic)   */
     int64_t launches;         /* kernels launched by this call                                                  */
     double sweep_kernel_ms;   /* CUDA-event time of the sweep kernel alone (device_ms also covers record set-up) */
     int64_t guard_hits;       /* draws whose margin was below the guard and were redone on the exact path (bgmm_set_guard) */
-    int64_t fast_steps;       /* data resolved by the register-resident sequential step (engine diagnostic)             */
+    int64_t fast_steps;       /* data resolved by a resident sequential step: the cluster step engines (and the data their
+                                 window kernel certified as stays) or the in-CTA register step (engine diagnostic)      */
 } bgmm_sweep_stats;
 
 const char *bgmm_version(void);

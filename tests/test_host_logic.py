@@ -96,3 +96,16 @@ def test_shard_bounds_and_label_offsets():
     z = [np.array([0, 1, 1, -1]), np.array([2, 0, 1]), np.array([0])]
     out = fanout.offset_labels(z, [2, 3, 1])
     assert out.tolist() == [0, 1, 1, -1, 4, 2, 3, 5]
+
+
+def test_betabern_struct():
+    """pybgmm/prior/betabern.py:8-18: fields a, b, the tag, the refusal of a negative a; SubCRPMM's starting inclusion
+    probability is the prior mean (subcrpmm.py:46-48)."""
+    from pybgmm_b200.prior import BetaBern
+    b = BetaBern(2, 6)
+    assert (b.name, b.a, b.b) == ("Beta", 2, 6)
+    assert b.mean() == 0.25
+    assert b.posterior(3, 1) == (5, 7)
+    import pytest
+    with pytest.raises(AssertionError):
+        BetaBern(-1, 1)
