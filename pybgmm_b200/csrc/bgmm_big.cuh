@@ -461,7 +461,8 @@ __global__ void __launch_bounds__(TB, 1) k_big_sweep(const Params p_in, double *
 // and everything behind it is evaluated again later (its weights may change with that datum's move).
 // Dynamic shared memory: big_window_smem<DP>().
 // ---------------------------------------------------------------------------------------------
-constexpr int WT = 32;   // positions per tile
+constexpr int WT = 64;   // positions per tile: every thread works on two of them (t and t + 32), so a staged element of B
+                         // loaded from shared memory feeds two FMAs
 
 template <int DP> constexpr size_t big_window_smem() {
     return sizeof(double) * ((size_t)DP * (DP + 2) + (size_t)DP * WT + (size_t)KCH * WT + 8 * WT + DP + NSC + fm::TAB_LEN);
@@ -533,29 +534,40 @@ __global__ void __launch_bounds__(256) k_big_window(const Params p, const double
             }
             for (int e = tid; e < DP + NSC; e += 256) mk[e] = __ldcg(rk + L::MU + e);
             __syncthreads();
-            double y[RPT];
+            double y0[RPT], y1[RPT];
 #pragma unroll
-            for (int r = 0; r < RPT; ++r) y[r] = 0.0;
+            for (int r = 0; r < RPT; ++r) { y0[r] = 0.0; y1[r] = 0.0; }
 #pragma unroll 4
             for (int b = 0; b < DP; ++b) {
-                const double d = mk[b] - Xs[b * WT + tx];
+                const double m = mk[b];
+                const double d0 = m - Xs[b * WT + tx], d1 = m - Xs[b * WT + 32 + tx];
 #pragma unroll
-                for (int r = 0; r < RPT; ++r) y[r] = fma(Bt[b * BS + ty * RPT + r], d, y[r]);
+                for (int r = 0; r < RPT; ++r) {
+                    const double bv = Bt[b * BS + ty * RPT + r];
+                    y0[r] = fma(bv, d0, y0[r]);
+                    y1[r] = fma(bv, d1, y1[r]);
+                }
             }
-            double part = 0.0;
+            double part0 = 0.0, part1 = 0.0;
 #pragma unroll
-            for (int r = 0; r < RPT; ++r) part = fma(mk[ty * RPT + r] - Xs[(ty * RPT + r) * WT + tx], y[r], part);
-            qp[ty * WT + tx] = part;
+            for (int r = 0; r < RPT; ++r) {
+                const double m = mk[ty * RPT + r];
+                part0 = fma(m - Xs[(ty * RPT + r) * WT + tx], y0[r], part0);
+                part1 = fma(m - Xs[(ty * RPT + r) * WT + 32 + tx], y1[r], part1);
+            }
+            qp[ty * WT + tx] = part0;
+            qp[ty * WT + 32 + tx] = part1;
             __syncthreads();
-            if (ty == 0) {
+            if (ty < 2) {
+                const int t = ty * 32 + tx;
                 double q = 0.0;
 #pragma unroll
-                for (int g = 0; g < 8; ++g) q += qp[g * WT + tx];
+                for (int g = 0; g < 8; ++g) q += qp[g * WT + t];
                 const double *sc = mk + DP;
-                const int own = (k == kos[tx]) ? 1 : 0;
-                double e = fast::f_finish_weight<1>(sc, q, own, p.log_alpha + lps[tx], fmt);
+                const int own = (k == kos[t]) ? 1 : 0;
+                double e = fast::f_finish_weight<1>(sc, q, own, p.log_alpha + lps[t], fmt);
                 if (own && sc[F_N] == 1.0) e = NAN;   // the datum is its component's last member: not a plain stay
-                E[k * WT + tx] = e;
+                E[k * WT + t] = e;
             }
         }
         __syncthreads();
