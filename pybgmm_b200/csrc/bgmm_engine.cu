@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -825,8 +826,12 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
         while (pos < h->N) {
             p.start_pos = pos;
             if (need_prep || use_clu || since_prep >= big::BIG_SPAN) {
+                std::chrono::steady_clock::time_point tp0;
+                const bool tprof = getenv("BGMM_WPROF") != nullptr && !use_clu;
+                if (tprof) { CU(cudaStreamSynchronize(st)); tp0 = std::chrono::steady_clock::now(); }
                 if (int rc = use_clu ? h->ops->clu_prep(h, p, c.K) : h->ops->big_prep(h, p, c.K)) return rc;
                 if (int rc = check_dev_err(h, "sweep (record set-up)")) return rc;
+                if (tprof) fprintf(stderr, "  prep: %.0f us\n", 1e6 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
                 need_prep = false;
                 since_prep = 0;
             }
@@ -877,13 +882,22 @@ static int run_sweep(bgmm_handle *h, const long long *d_order, const double *d_u
                 // the generic engine's (Cholesky) records follow from the statistics; its step resolves the datum
                 handbacks += 1;
                 c.error = 0;
+                const bool tprof = getenv("BGMM_WPROF") != nullptr;
+                std::chrono::steady_clock::time_point t0, t1, t2;
+                if (tprof) { CU(cudaStreamSynchronize(st)); t0 = std::chrono::steady_clock::now(); }
                 CU(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
                 if (int rc = h->ops->refactor_all(h, p, 0, c.K)) return rc;
                 h->launches += 1;
                 need_prep = true;
+                if (tprof) { CU(cudaStreamSynchronize(st)); t1 = std::chrono::steady_clock::now(); }
                 if (int rc = h->ops->resolve_one(h, p, pos)) return rc;
                 CU(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
                 CU(cudaStreamSynchronize(st));
+                if (tprof) {
+                    t2 = std::chrono::steady_clock::now();
+                    fprintf(stderr, "  hand-back at %lld: refactor_all %.0f us, resolve_one %.0f us\n", pos,
+                            1e6 * std::chrono::duration<double>(t1 - t0).count(), 1e6 * std::chrono::duration<double>(t2 - t1).count());
+                }
                 pos = c.pos;
                 if (c.error != 0) break;
                 if (c.K < 1 || c.K > (use_clu ? clu::KCH - 1 : h->Kcap)) { to_generic = true; break; }

@@ -2,7 +2,7 @@
 # N-GPU bench lines (torchrun, one rank per GPU): c3 independent chains, c5 disjoint shards, c4 independent chains
 N=${1:-2}
 mkdir -p gpurun_out
-for wl in c3 c5 c4; do
+for wl in ${WLS:-c3 c5 c4}; do
   steps=6; [ $wl = c4 ] && steps=4
   NCCL_DEBUG=INFO timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N \
      bench.py --gpus $N --workload $wl --steps $steps --warmup 3 > gpurun_out/bench_${wl}_${N}gpu.json 2> gpurun_out/bench_${wl}_${N}gpu.err
