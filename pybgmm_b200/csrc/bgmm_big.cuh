@@ -516,6 +516,13 @@ __global__ void __launch_bounds__(256) k_big_window(const Params p, const double
             const long long i = js[t];
             Xs[b * WT + t] = i >= 0 ? p.X[(size_t)i * DP + b] : 0.0;
         }
+        // component k + 1's packed triangle, mean and scalars travel from L2 into registers while component k is being
+        // multiplied: the staging below is shared-memory stores only
+        constexpr int NPRE = (L::PP + 255) / 256;
+        double pre[NPRE], premk = 0.0;
+#pragma unroll
+        for (int t = 0; t < NPRE; ++t) pre[t] = (K > 0 && tid + t * 256 < L::PP) ? __ldcg(rec_in + tid + t * 256) : 0.0;
+        if (K > 0 && tid < DP + NSC) premk = __ldcg(rec_in + L::MU + tid);
         for (int k = 0; k < K; ++k) {
             __syncthreads();
             if ((k & 7) == 7) {   // an earlier position ended the window meanwhile: this tile's answer is not needed
@@ -523,17 +530,25 @@ __global__ void __launch_bounds__(256) k_big_window(const Params p, const double
                 __syncthreads();
                 if (stop_s) break;
             }
-            const double *rk = rec_in + (size_t)k * R;
-            for (int e = tid; e < L::PP; e += 256) {   // the packed triangle (lane-interleaved rows, see pidx) -> full matrix
-                const int ln = e % NL, j = e / NL;
-                int a, b;
-                if (j <= ln) { a = ln; b = j; } else { a = DP - 1 - ln; b = j - ln - 1; }
-                const double v = __ldcg(rk + e);
-                Bt[b * BS + a] = v;
-                Bt[a * BS + b] = v;
+#pragma unroll
+            for (int t = 0; t < NPRE; ++t) {   // the packed triangle (lane-interleaved rows, see pidx) -> full matrix
+                const int e = tid + t * 256;
+                if (e < L::PP) {
+                    const int ln = e % NL, j = e / NL;
+                    int a, b;
+                    if (j <= ln) { a = ln; b = j; } else { a = DP - 1 - ln; b = j - ln - 1; }
+                    Bt[b * BS + a] = pre[t];
+                    Bt[a * BS + b] = pre[t];
+                }
             }
-            for (int e = tid; e < DP + NSC; e += 256) mk[e] = __ldcg(rk + L::MU + e);
+            if (tid < DP + NSC) mk[tid] = premk;
             __syncthreads();
+            if (k + 1 < K) {
+                const double *rn = rec_in + (size_t)(k + 1) * R;
+#pragma unroll
+                for (int t = 0; t < NPRE; ++t) pre[t] = (tid + t * 256 < L::PP) ? __ldcg(rn + tid + t * 256) : 0.0;
+                if (tid < DP + NSC) premk = __ldcg(rn + L::MU + tid);
+            }
             double y0[RPT], y1[RPT];
 #pragma unroll
             for (int r = 0; r < RPT; ++r) { y0[r] = 0.0; y1[r] = 0.0; }
