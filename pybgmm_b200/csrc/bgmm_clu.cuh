@@ -403,36 +403,31 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             const NS nsx = ns_of((sel == 1) ? dn : 0);
             const double rk = side ? -rkw[3] : rkw[1];   // m' = m -+ d_s / kappa(n2), d_s = m - x_s
             CLU_T(4);   // scalars of the other outcome
-            double e_u = 0.0, e_a = 0.0, q_u = 0.0, q_a = 0.0, sg = 0.0, w = 0.0, al_lds = lds;
+            // (past the last datum of the launch the ring slot holds stale data: evaluated like any other, never sent)
+            double e_u, e_a, q_u, q_a, sg, w, al_lds;
             {
-                int own1 = 0;
-                double wref1 = 0.0, x = den;
-                if (has_next) {
-                    double sg_u;
-                    quad(cur_v, slot1, q_u, sg_u, w);
-                    sg = fma(rk, cur_q, sg_u);
-                    q_a = fma(gam * sg, sg, fma(rk, fma(rk, cur_q, 2.0 * sg_u), q_u));
-                    own1 = (k == S.kor[slot1]) ? 1 : 0;
-                    wref1 = p.log_alpha + S.lpr[slot1];
-                    const double q_sel = (sel == 1) ? q_a : q_u;
-                    const double arg = own1 ? fma(-nsx.beta, q_sel, 1.0) : fma(nsx.g, q_sel, 1.0);
-                    x = (sel == 2) ? den : arg;
-                }
+                double sg_u;
+                quad(cur_v, slot1, q_u, sg_u, w);
+                sg = fma(rk, cur_q, sg_u);
+                q_a = fma(gam * sg, sg, fma(rk, fma(rk, cur_q, 2.0 * sg_u), q_u));
+                const int own1 = (k == S.kor[slot1]) ? 1 : 0;
+                const double wref1 = p.log_alpha + S.lpr[slot1];
+                const double q_sel = (sel == 1) ? q_a : q_u;
+                const double arg = own1 ? fma(-nsx.beta, q_sel, 1.0) : fma(nsx.g, q_sel, 1.0);
+                const double x = (sel == 2) ? den : arg;
                 CLU_T(5);   // quadratic forms
                 // one logarithm for the three arguments (the two weights' and the determinant lemma's), one exponential
                 const double Lg = c_log(x, S.fm);
                 al_lds = lds + __shfl_sync(0xffffffffu, Lg, 2);
                 CLU_T(6);   // logarithm
-                if (has_next) {
-                    const double lds_sel = (sel == 1) ? al_lds : lds;
-                    const double cc = (own1 ? nsx.cn_m : nsx.cn_n) - 0.5 * lds_sel, hh = own1 ? 1.0 - nsx.hh : nsx.hh;
-                    const double tt = (cc - hh * Lg) - wref1;
-                    double e = (tt < EXP_CUTOFF) ? 0.0 : c_exp(tt, S.fm);
-                    // the own component's closed form is not trusted / the datum is its last member: the general step
-                    if (own1 && (!(x > OM_MIN) || n_sel == 1.0)) e = NAN;
-                    e_u = __shfl_sync(0xffffffffu, e, 0);
-                    e_a = alt_ok ? __shfl_sync(0xffffffffu, e, 1) : NAN;
-                }
+                const double lds_sel = (sel == 1) ? al_lds : lds;
+                const double cc = (own1 ? nsx.cn_m : nsx.cn_n) - 0.5 * lds_sel, hh = own1 ? 1.0 - nsx.hh : nsx.hh;
+                const double tt = (cc - hh * Lg) - wref1;
+                double e = (tt < EXP_CUTOFF) ? 0.0 : c_exp(tt, S.fm);
+                // the own component's closed form is not trusted / the datum is its last member: the general step
+                if (own1 && (!(x > OM_MIN) || n_sel == 1.0)) e = NAN;
+                e_u = __shfl_sync(0xffffffffu, e, 0);
+                e_a = alt_ok ? __shfl_sync(0xffffffffu, e, 1) : NAN;
             }
             CLU_T(1);   // preparation of datum s + 1
             // the draw of datum s
