@@ -375,16 +375,16 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             if (own0 && n == 1.0) e = NAN;   // the datum is its component's last member: the general step
             if (lane == 0) st_async_u64(e_dst, (unsigned long long)__double_as_longlong(e), e_bar);
         }
-        for (long long s = 0; s < total; ++s) {
-            const int slot = (int)(s & (RS - 1)), slot1 = (int)((s + 1) & (RS - 1));
-            const bool has_next = s + 1 < total;
+        const int n_steps = (int)total;   // a launch covers at most BIG_SPAN data
+        for (int s = 0; s < n_steps; ++s) {
+            const int slot = s & (RS - 1), slot1 = (s + 1) & (RS - 1);
+            const bool has_next = s + 1 < n_steps;
             const int ko = S.kor[slot];
             if (pend && --pend == 0) { tw = tw2; wc = wc2; }
-            if (s > 0 && (s & 31) == 0) {   // done with the previous half of the ring (its last datum was committed)
-                if (lane == 0) mbar_arrive(&S.empty[((s - 1) >> 5) & 1]);
-            }
-            if (has_next && ((s + 1) & 31) == 0) {
-                const long long ch = (s + 1) >> 5;
+            if ((s & 31) == 0 && s > 0 && lane == 0)   // done with the previous half of the ring (its last datum was committed)
+                mbar_arrive(&S.empty[((s - 1) >> 5) & 1]);
+            if (((s + 1) & 31) == 0 && has_next) {
+                const int ch = (s + 1) >> 5;
                 while (!mbar_try_wait(&S.full[ch & 1], (unsigned)((ch >> 1) & 1))) wd.poll(ctl, 12);
             }
             CLU_T(0);   // ring
@@ -435,10 +435,11 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             const unsigned long long res = *(volatile unsigned long long *)&S.res;
             __syncwarp();
             if (armer && lane == 0) mbar_arrive_expect_tx(&S.rbar, 8);   // next phase
-            const int k_new = (int)(res & 0xffffu), rare = (int)((res >> 16) & 0xffu), stop_after = (int)((res >> 24) & 1u);
-            if (rare) break;
-            const bool touched = (k_new != ko) && (k == ko || k == k_new);
-            if (has_next && !stop_after && lane == 0)
+            const int k_new = (int)(res & 0xffffu);
+            const unsigned ending = (unsigned)(res >> 16) & 0x1ffu;   // rare code (the datum is not resolved here) | stop_after << 8
+            const bool rare = (ending & 0xffu) != 0u;
+            const bool touched = !rare && (k_new != ko) && (k == ko || k == k_new);
+            if (ending == 0u && has_next && lane == 0)
                 st_async_u64(e_dst, (unsigned long long)__double_as_longlong(touched ? e_a : e_u), e_bar);
             CLU_T(2);   // waiting for the draw
             if (touched) {
@@ -460,14 +461,11 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
                 ns_st = ns_of(0);
                 const long long n_now = (long long)n;
                 if (pend == 0 && (n_now - wc >= 3 || wc - n_now >= 3)) { wc2 = n_now; tw2 = fetch_win(n_now); pend = 2; }
-                cur_v = fma(fma(gam, sg, rk), cur_v, w);   // B' d' = B d + (rk + gam sigma) v
-                cur_q = q_a;
                 CLU_T(3);   // commit
-            } else {
-                cur_v = w;
-                cur_q = q_u;
             }
-            if (stop_after) break;
+            cur_v = touched ? fma(fma(gam, sg, rk), cur_v, w) : w;   // B' d' = B d + (rk + gam sigma) v
+            cur_q = touched ? q_a : q_u;
+            if (ending) break;
         }
         if (warp == 0 && c <= 2) CLU_TFLUSH(c);
         if (warp == n_comp_warps - 1 && c == 1) CLU_TFLUSH(3);
