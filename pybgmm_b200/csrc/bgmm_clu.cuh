@@ -433,14 +433,14 @@ __global__ void __launch_bounds__(CL<DP>::TB, 1) k_clu_sweep(const Params p, con
             // the draw of datum s
             while (!mbar_try_wait_cluster(&S.rbar, (unsigned)(s & 1))) wd.poll(ctl, 13);
             const unsigned long long res = *(volatile unsigned long long *)&S.res;
-            __syncwarp();
-            if (armer && lane == 0) mbar_arrive_expect_tx(&S.rbar, 8);   // next phase
             const int k_new = (int)(res & 0xffffu);
             const unsigned ending = (unsigned)(res >> 16) & 0x1ffu;   // rare code (the datum is not resolved here) | stop_after << 8
             const bool rare = (ending & 0xffu) != 0u;
             const bool touched = !rare && (k_new != ko) && (k == ko || k == k_new);
-            if (ending == 0u && has_next && lane == 0)
+            if (ending == 0u && has_next && lane == 0)   // first thing after the result: the chain waits for this store
                 st_async_u64(e_dst, (unsigned long long)__double_as_longlong(touched ? e_a : e_u), e_bar);
+            __syncwarp();
+            if (armer && lane == 0) mbar_arrive_expect_tx(&S.rbar, 8);   // next phase
             CLU_T(2);   // waiting for the draw
             if (touched) {
                 // the component takes the other outcome: B += gam v v', m += rk (m - x_s)
